@@ -1,0 +1,17 @@
+import torch
+
+
+class FrechetInceptionDistance:
+    """NaN-returning stand-in (see package docstring)."""
+
+    def __init__(self, *args, **kwargs):
+        pass
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def update(self, *args, **kwargs):
+        pass
+
+    def compute(self):
+        return torch.tensor(float("nan"))
