@@ -1,0 +1,69 @@
+// Host-side helpers shared by the launchers: TMA tensor-map creation (driver entry point fetched at run time so
+// the library does not link libcuda) with a small cache, plus library-level C-ABI utilities.
+#include "common.cuh"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace mdgan {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int get_tmap_2d_f32(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, CUtensorMap* out) {
+  using Key = std::tuple<const void*, uint64_t, uint64_t, uint32_t>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  Key key{ptr, rows, cols, box_rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MDGAN_ERR_DRIVER;
+  if (cols % 32 != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || box_rows == 0 || box_rows > 256)
+    return MDGAN_ERR_BAD_ARG;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return MDGAN_ERR_DRIVER;
+  cache[key] = m;
+  *out = m;
+  return 0;
+}
+
+}  // namespace mdgan
+
+extern "C" int mdgan_abi_version(void) { return 1; }
+
+// Which SM architecture the loaded device code targets and whether the current device can run it.
+// Returns 0 when the current CUDA device is compute capability 10.x, MDGAN_ERR_UNSUPPORTED otherwise.
+extern "C" int mdgan_check_device(void) {
+  int dev = 0;
+  MDGAN_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  MDGAN_CUDA(cudaGetDeviceProperties(&prop, dev));
+  return prop.major == 10 ? 0 : MDGAN_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,268 @@
+// Weight-gradient implicit GEMM for the "k4 s2 p1" layer family, tcgen05 (kind::tf32, both operands MN-major).
+//
+//   dW_tap[c1, c2] = sum over low-res positions p=(n,i,j) of  Lo[p, c1] * Hi[(n, 2i-1+kh, 2j-1+kw), c2]
+//
+// which is the weight gradient of both Conv2d(k4,s2,p1) (Lo = grad of the conv output, Hi = conv input;
+// result [c1=co][c2=ci]) and ConvTranspose2d(k4,s2,p1) (Lo = convT input, Hi = grad of the convT output;
+// result [c1=ci][c2=co]) -- the autograd work behind /root/reference/src/actors/worker.py:204 and
+// /root/reference/src/actors/server.py:286-292.  mode 2 (identity gather, 1 tap) is the weight gradient of
+// the generator's first layer (ConvTranspose2d on a 1x1 input = plain GEMM).
+//
+// The reduction dimension is the pixel index, which is the slow dimension of both NHWC operands, so both smem
+// operands are MN-major: a stage holds 32 pixels; each 32-channel group is a [32 pixel rows x 128 B] block in the
+// SWIZZLE_128B_BASE32B layout (4-row atoms, 32-byte swizzle granularity -- the only MN-major layout tcgen05
+// accepts for 32-bit operands).  One tcgen05.mma (K = 8 pixels) consumes two 4-row atoms of every group.
+// Split-K over pixels fills the machine; partial sums go to [split][tap][C1][C2] and are reduced (in a fixed
+// order, deterministically) by the unpack kernel in elementwise.cu.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mdgan {
+
+struct WgradParams {
+  const float* lo;  // NHWC [n_img, Hl, Wl, C1]
+  const float* hi;  // NHWC [n_img, Hh, Wh, C2]  (Hh = 2*Hl for mode 0; = Hl for mode 2)
+  float* partial;   // [splits][taps][C1][C2]
+  int n_img, Hl, Wl, Hh, Wh, C1, C2;
+  int mode;         // 0: k4 s2 p1 gather (16 taps), 2: identity (1 tap)
+  int P;            // n_img*Hl*Wl
+  int splits, pix_per_split;
+  int lbo_a, sbo_a, lbo_b, sbo_b;  // descriptor byte offsets (see file header)
+};
+
+constexpr int kWM = 128;
+constexpr int kWK = 32;  // pixels per stage
+constexpr int kWProducerWarps = 8;
+constexpr int kWThreads = (kWProducerWarps + 1) * 32;
+
+// Byte offset of 16-byte chunk `c16` (0..7) of pixel row `r` inside its 128-byte row under SWIZZLE_128B_BASE32B:
+// the 32-byte chunk index is XORed with (row & 3).
+__device__ __forceinline__ uint32_t swz32(int c16, int r) {
+  return static_cast<uint32_t>(((((c16 >> 1) ^ (r & 3)) << 5) | ((c16 & 1) << 4)));
+}
+
+template <int BN, int STAGES>
+struct WgradSmem {
+  static constexpr int kABytes = (kWM / 32) * kWK * 128;
+  static constexpr int kBBytes = (BN / 32) * kWK * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradParams p) {
+  using S = WgradSmem<BN, STAGES>;
+  constexpr int LAG = STAGES - 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int c1_0 = blockIdx.x * kWM;
+  const int c2_0 = blockIdx.y * BN;
+  const int tap = blockIdx.z / p.splits;
+  const int split = blockIdx.z - tap * p.splits;
+  const int pix0 = split * p.pix_per_split;
+  const int pix1 = min(p.P, pix0 + p.pix_per_split);
+  const int ksteps = (pix1 > pix0) ? (pix1 - pix0 + kWK - 1) / kWK : 0;
+  const int dh = (p.mode == 0) ? (tap >> 2) - 1 : 0;
+  const int dw = (p.mode == 0) ? (tap & 3) - 1 : 0;
+  const int SI = (p.mode == 0) ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], kWProducerWarps * 32);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == kWProducerWarps) tmem_alloc<BN>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < kWProducerWarps) {
+    // ---------------------------------------------------------------- producers (both operands)
+    const uint32_t smem0 = smem_u32(smem);
+    // A (Lo): 32 chunks of 16 B per pixel row (4 groups x 8 chunks); thread -> (cidx = tid%32, rows tid/32 + 8i)
+    const int a_cidx = threadIdx.x & 31;
+    const int a_row0 = threadIdx.x >> 5;
+    // B (Hi): BN/4 chunks per pixel row
+    constexpr int kBChunksPerRow = BN / 4;
+    constexpr int kBRowsPerPass = 256 / kBChunksPerRow;
+    constexpr int kBPasses = kWK / kBRowsPerPass;
+    const int b_cidx = threadIdx.x % kBChunksPerRow;
+    const int b_row0 = threadIdx.x / kBChunksPerRow;
+    const int hw_l = p.Hl * p.Wl;
+    for (int it = 0; it < ksteps; ++it) {
+      const int s = it % STAGES;
+      const uint32_t par = (it / STAGES) & 1;
+      mbar_wait(&empty_bar[s], par ^ 1);
+      const uint32_t a_stage = smem0 + s * S::kStageBytes;
+      const uint32_t b_stage = a_stage + S::kABytes;
+      const int pbase = pix0 + it * kWK;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = a_row0 + 8 * i;
+        const int pix = pbase + r;
+        const bool ok = pix < pix1;
+        const float* g = p.lo + (ok ? (static_cast<size_t>(pix) * p.C1 + c1_0 + a_cidx * 4) : 0);
+        const uint32_t d = a_stage + (a_cidx >> 3) * (kWK * 128) + r * 128 + swz32(a_cidx & 7, r);
+        cp_async_16(d, g, ok ? 16u : 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < kBPasses; ++i) {
+        const int r = b_row0 + kBRowsPerPass * i;
+        const int pix = pbase + r;
+        bool ok = pix < pix1;
+        size_t off = 0;
+        if (ok) {
+          const int img = pix / hw_l;
+          const int rem = pix - img * hw_l;
+          const int gi = rem / p.Wl, gj = rem - gi * p.Wl;
+          const int sh = gi * SI + dh, sw = gj * SI + dw;
+          ok = sh >= 0 && sh < p.Hh && sw >= 0 && sw < p.Wh;
+          off = (static_cast<size_t>((img * p.Hh + sh) * p.Wh + sw)) * p.C2 + c2_0 + b_cidx * 4;
+        }
+        const float* g = p.hi + (ok ? off : 0);
+        const uint32_t d = b_stage + (b_cidx >> 3) * (kWK * 128) + r * 128 + swz32(b_cidx & 7, r);
+        cp_async_16(d, g, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (it >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async_smem();
+        mbar_arrive(&full_bar[(it - LAG) % STAGES]);
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (int it = (ksteps > LAG ? ksteps - LAG : 0); it < ksteps; ++it) mbar_arrive(&full_bar[it % STAGES]);
+
+    // ---------------------------------------------------------------- epilogue: TMEM -> partial[split][tap]
+    if (ksteps > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after_sync();
+    }
+    const int q = warp & 3, half = warp >> 2;
+    constexpr int kColsPerHalf = BN / 2;
+    const int c1 = c1_0 + q * 32 + lane;
+    const int taps = gridDim.z / p.splits;
+    float* orow = p.partial + (static_cast<size_t>(split * taps + tap) * p.C1 + c1) * p.C2 + c2_0;
+#pragma unroll 1
+    for (int c16 = 0; c16 < kColsPerHalf; c16 += 16) {
+      const int col = half * kColsPerHalf + c16;
+      float v[16];
+      if (ksteps > 0) {
+        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+      if (c1 < p.C1) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(orow + col + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    tc_fence_before_sync();
+  } else {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kWM, BN, 1, 1);
+      for (int it = 0; it < ksteps; ++it) {
+        const int s = it % STAGES;
+        const uint32_t par = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], par);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
+        const uint32_t b_addr = a_addr + S::kABytes;
+#pragma unroll
+        for (int k = 0; k < kWK / 8; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a_addr + k * 1024, p.lbo_a, p.sbo_a, 1);
+          const uint64_t db = make_smem_desc_sw128(b_addr + k * 1024, p.lbo_b, p.sbo_b, 1);
+          umma_tf32(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      if (ksteps > 0) umma_commit(tmem_full_bar);
+    }
+  }
+  __syncthreads();
+  if (warp == kWProducerWarps) {
+    tc_fence_after_sync();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
+  using S = WgradSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    MDGAN_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    S::kDynamic));
+    configured = true;
+  }
+  wgrad_gemm_kernel<BN, STAGES><<<grid, kWThreads, S::kDynamic, st>>>(p);
+  MDGAN_CHECK_LAUNCH();
+  return 0;
+}
+
+// Debug override of the MN-major descriptor offsets (0 = use defaults); used once on hardware to confirm the
+// encoding, kept as a C-ABI knob for the parity tests.
+static int g_dbg_lbo = 0, g_dbg_sbo = 0;
+
+}  // namespace mdgan
+
+using namespace mdgan;
+
+extern "C" void mdgan_debug_set_wgrad_desc(int lbo_bytes, int sbo_bytes) {
+  g_dbg_lbo = lbo_bytes;
+  g_dbg_sbo = sbo_bytes;
+}
+
+// Number of split-K partial slices mdgan_wgrad_gemm will write for this problem (the caller sizes `partial`
+// as splits * taps * C1 * C2 floats).
+extern "C" int mdgan_wgrad_splits(int n_img, int Hl, int Wl, int C1, int C2, int mode) {
+  const int P = n_img * Hl * Wl;
+  const int taps = mode == 0 ? 16 : 1;
+  const int bn = (C2 % 128 == 0) ? 128 : 64;
+  const int tiles = (C1 / kWM) * (C2 / bn) * taps;
+  int splits = tiles >= 148 ? 1 : (148 + tiles - 1) / tiles;
+  const int max_splits = (P + 4 * kWK - 1) / (4 * kWK);  // at least 128 pixels per split
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+extern "C" int mdgan_wgrad_gemm(const float* lo, const float* hi, float* partial, int n_img, int Hl, int Wl, int C1,
+                                int C2, int mode, int splits, void* stream) {
+  if (!lo || !hi || !partial) return MDGAN_ERR_BAD_ARG;
+  if (C1 % kWM != 0 || C2 % 64 != 0 || (mode != 0 && mode != 2) || splits < 1) return MDGAN_ERR_UNSUPPORTED;
+  WgradParams p{};
+  p.lo = lo; p.hi = hi; p.partial = partial;
+  p.n_img = n_img; p.Hl = Hl; p.Wl = Wl;
+  p.Hh = mode == 0 ? 2 * Hl : Hl;
+  p.Wh = mode == 0 ? 2 * Wl : Wl;
+  p.C1 = C1; p.C2 = C2; p.mode = mode;
+  p.P = n_img * Hl * Wl;
+  p.splits = splits;
+  p.pix_per_split = ceil_div(ceil_div(p.P, splits), kWK) * kWK;
+  p.lbo_a = p.lbo_b = g_dbg_lbo ? g_dbg_lbo : kWK * 128;  // distance between 32-channel groups
+  p.sbo_a = p.sbo_b = g_dbg_sbo ? g_dbg_sbo : 512;        // distance between 4-pixel swizzle atoms
+  const int taps = mode == 0 ? 16 : 1;
+  const int bn = (C2 % 128 == 0) ? 128 : 64;
+  dim3 grid(C1 / kWM, C2 / bn, taps * splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bn == 128) return launch_wgrad<128, 4>(p, grid, st);
+  return launch_wgrad<64, 4>(p, grid, st);
+}

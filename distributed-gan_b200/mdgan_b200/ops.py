@@ -1,0 +1,196 @@
+"""Tensor-level wrappers over the C-ABI launchers (one function per exported kernel family).
+
+Activations are NHWC fp32 CUDA tensors, parameters keep their PyTorch layout.  Every wrapper launches on
+torch's current CUDA stream, so the calls can be captured into a CUDA graph.  No fallback: a non-CUDA tensor
+or a failed launch raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+MODE_DOWN, MODE_UP, MODE_DENSE = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.MdganLibraryError("MD-GAN kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise _lib.MdganLibraryError("MD-GAN kernels need contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _pad(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def n_pad_for(n: int) -> int:
+    """Packed-weight row padding: a multiple of the narrowest tensor-core tile (16)."""
+    return _pad(n, 16) if n < 32 else _pad(n, 32)
+
+
+# ----------------------------------------------------------------------------- weights
+def pack_down(W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """W [N, C, 4, 4] -> [N_pad, 16*C_pad] (K-major, K = (tap, c)); conv fwd / convT dgrad operand."""
+    N, Cc = W.shape[0], W.shape[1]
+    Np, Cp = n_pad_for(N), _pad(Cc, 32)
+    if out is None:
+        out = torch.empty((Np, 16 * Cp), device=W.device, dtype=torch.float32)
+    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 0, N, Cc, Np, Cp, 16, _stream()), "pack_down")
+    return out
+
+
+def pack_up(W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """W [C, N, 4, 4] -> [4 phases * N_pad, 4*C_pad]; convT fwd / conv dgrad operand."""
+    Cc, N = W.shape[0], W.shape[1]
+    Np, Cp = n_pad_for(N), _pad(Cc, 32)
+    if out is None:
+        out = torch.empty((4 * Np, 4 * Cp), device=W.device, dtype=torch.float32)
+    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 1, N, Cc, Np, Cp, 16, _stream()), "pack_up")
+    return out
+
+
+def pack_dense(W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """W [C, N, k, k] (ConvTranspose2d on a 1x1 input) -> [k*k*N, C_pad]."""
+    Cc, N, KK = W.shape[0], W.shape[1], W.shape[2] * W.shape[3]
+    Cp = _pad(Cc, 32)
+    if out is None:
+        out = torch.empty((KK * N, Cp), device=W.device, dtype=torch.float32)
+    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 2, N, Cc, KK * N, Cp, KK, _stream()), "pack_dense")
+    return out
+
+
+# ----------------------------------------------------------------------------- tensor-core GEMMs
+def conv_gemm(src: torch.Tensor, wpacked: torch.Tensor, mode: int, N: int, out: torch.Tensor,
+              grid: Tuple[int, int, int], src_hw: Tuple[int, int], bias: Optional[torch.Tensor] = None,
+              out_nchw: bool = False, act_tanh: bool = False, round_tf32: bool = False, force_bn: int = 0) -> torch.Tensor:
+    """grid = (n_img, Hg, Wg): the low-resolution row grid; src is NHWC [n_img, Hs, Ws, C]."""
+    n_img, Hg, Wg = grid
+    Hs, Ws = src_hw
+    Cc = src.shape[-1]
+    phases = 4 if mode == MODE_UP else 1
+    N_pad = wpacked.shape[0] // phases
+    rc = _lib.load().mdgan_conv_gemm(_ptr(src), _ptr(wpacked), _ptr(out), _ptr(bias), n_img, Hg, Wg, Hs, Ws, Cc, mode,
+                                     N, N_pad, int(out_nchw), int(act_tanh), int(round_tf32), force_bn, _stream())
+    _lib.check(rc, "conv_gemm")
+    return out
+
+
+def wgrad_splits(n_img: int, Hl: int, Wl: int, C1: int, C2: int, mode: int) -> int:
+    return _lib.load().mdgan_wgrad_splits(n_img, Hl, Wl, C1, C2, mode)
+
+
+def wgrad_gemm(lo: torch.Tensor, hi: torch.Tensor, partial: torch.Tensor, grid: Tuple[int, int, int], mode: int,
+               splits: int) -> torch.Tensor:
+    n_img, Hl, Wl = grid
+    rc = _lib.load().mdgan_wgrad_gemm(_ptr(lo), _ptr(hi), _ptr(partial), n_img, Hl, Wl, lo.shape[-1], hi.shape[-1],
+                                      mode, splits, _stream())
+    _lib.check(rc, "wgrad_gemm")
+    return partial
+
+
+def wgrad_unpack(partial: torch.Tensor, grad: torch.Tensor, mode: int, splits: int, C1: int, C1p: int, C2: int,
+                 N: int = 0, KK: int = 0) -> torch.Tensor:
+    rc = _lib.load().mdgan_wgrad_unpack(_ptr(partial), _ptr(grad), mode, splits, C1, C1p, C2, N, KK, _stream())
+    _lib.check(rc, "wgrad_unpack")
+    return grad
+
+
+def reduce_slices(partial: torch.Tensor, out: torch.Tensor, slices: int) -> torch.Tensor:
+    _lib.check(_lib.load().mdgan_reduce_slices(_ptr(partial), _ptr(out), slices, out.numel(), _stream()), "reduce_slices")
+    return out
+
+
+# ----------------------------------------------------------------------------- thin (image-side) layers
+def thin_down(img: torch.Tensor, W: torch.Tensor, out: torch.Tensor, act: int = ACT_NONE, slope: float = 0.0,
+              round_tf32: bool = False) -> torch.Tensor:
+    n, ci, Hi, Wi = img.shape
+    rc = _lib.load().mdgan_thin_down(_ptr(img), _ptr(W), _ptr(out), n, ci, Hi, Wi, W.shape[0], act, slope,
+                                     int(round_tf32), _stream())
+    _lib.check(rc, "thin_down")
+    return out
+
+
+def thin_wgrad_slices(n_img: int, Hl: int, Wl: int) -> int:
+    return _lib.load().mdgan_thin_wgrad_slices(n_img, Hl, Wl)
+
+
+def thin_wgrad(feat: torch.Tensor, img: torch.Tensor, partial: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
+    n, ci, Hi, Wi = img.shape
+    Hl, Wl, C1 = Hi // 2, Wi // 2, feat.shape[-1]
+    lib = _lib.load()
+    _lib.check(lib.mdgan_thin_wgrad(_ptr(feat), _ptr(img), _ptr(partial), n, ci, Hl, Wl, C1, _stream()), "thin_wgrad")
+    return reduce_slices(partial, grad, thin_wgrad_slices(n, Hl, Wl))
+
+
+# ----------------------------------------------------------------------------- BatchNorm + activation
+def bn_workspace_floats(G: int, Pg: int, Cc: int) -> int:
+    return _lib.load().mdgan_bn_workspace_floats(G, Pg, Cc)
+
+
+def bn_forward(x, out, gamma, beta, running_mean, running_var, nbt, stats, workspace, G, Pg, Cc, act, slope,
+               round_tf32=False, eps=1e-5, momentum=0.1):
+    rc = _lib.load().mdgan_bn_forward(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                                      _ptr(nbt), _ptr(stats), _ptr(workspace), G, Pg, Cc, eps, momentum, act, slope,
+                                      int(round_tf32), _stream())
+    _lib.check(rc, "bn_forward")
+    return out
+
+
+def bn_backward(da, x, stats, dx, dgamma, dbeta, sums, workspace, G, Pg, Cc, act, slope, round_tf32=False):
+    rc = _lib.load().mdgan_bn_backward(_ptr(da), _ptr(x), _ptr(stats), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(sums),
+                                       _ptr(workspace), G, Pg, Cc, act, slope, int(round_tf32), _stream())
+    _lib.check(rc, "bn_backward")
+    return dx
+
+
+def act_backward(da, a, dz, act, slope, round_tf32=False):
+    _lib.check(_lib.load().mdgan_act_backward(_ptr(da), _ptr(a), _ptr(dz), a.numel(), act, slope, int(round_tf32),
+                                              _stream()), "act_backward")
+    return dz
+
+
+def tanh_backward(s, x, out, scale: float):
+    _lib.check(_lib.load().mdgan_tanh_backward(_ptr(s), _ptr(x), _ptr(out), x.numel(), scale, _stream()), "tanh_backward")
+    return out
+
+
+# ----------------------------------------------------------------------------- head / loss / optimiser
+def head_forward(a, w, label, prob, loss_terms, dlogit, loss, G, b, HW, Cc):
+    rc = _lib.load().mdgan_head_forward(_ptr(a), _ptr(w), _ptr(label), _ptr(prob), _ptr(loss_terms), _ptr(dlogit),
+                                        _ptr(loss), G, b, HW, Cc, _stream())
+    _lib.check(rc, "head_forward")
+
+
+def head_backward(a, w, dlogit, da, dw, n_total, HW, Cc):
+    rc = _lib.load().mdgan_head_backward(_ptr(a), _ptr(w), _ptr(dlogit), _ptr(da), _ptr(dw), n_total, HW, Cc, _stream())
+    _lib.check(rc, "head_backward")
+
+
+def adam_step(p, g, m, v, step_count, lr, beta1, beta2, eps=1e-8):
+    rc = _lib.load().mdgan_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(step_count), lr, beta1, beta2,
+                                     eps, _stream())
+    _lib.check(rc, "adam_step")
+
+
+def pad_rows(x, out, round_tf32=False):
+    rows, cin = x.shape
+    _lib.check(_lib.load().mdgan_pad_rows(_ptr(x), _ptr(out), rows, cin, out.shape[1], int(round_tf32), _stream()),
+               "pad_rows")
+    return out
+
+
+def sum_slices(x, out, count: int, stride: int):
+    _lib.check(_lib.load().mdgan_sum_slices(_ptr(x), _ptr(out), out.numel(), count, stride, _stream()), "sum_slices")
+    return out

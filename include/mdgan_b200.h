@@ -1,0 +1,133 @@
+/* mdgan_b200.h -- C ABI of libmdgan_b200.so, the sm_100a kernel library behind the MD-GAN training step.
+ *
+ * The reference (owengombas/distributed-gan) has no native code and no FFI: every number on its hot path is
+ * produced by a torch library call made from src/actors/{server,worker}.py and the model files
+ * src/datasets/{CIFAR10,CelebA,MNIST}.py.  Each entry point below therefore names the torch call site(s) it
+ * replaces (reference file:line, relative to /root/reference).  The binding a maintainer would add on the
+ * reference side is a ctypes stub (Python is the reference's own language); see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers to fp32 unless stated otherwise;
+ *   - activations are NHWC contiguous, image-side tensors (real / generated batches, feedback) NCHW contiguous,
+ *     parameters keep the PyTorch layout of the reference's state_dict;
+ *   - `stream` is a cudaStream_t (0 = default stream); launches are asynchronous and stream-ordered, the
+ *     library keeps no global state besides a tensor-map cache and is safe to capture into a CUDA graph;
+ *   - every launcher returns int: 0 = ok, > 0 = cudaError_t, < 0 = MDGAN_ERR_* below.  Nothing throws, nothing
+ *     falls back to another implementation: unsupported shapes are errors.
+ *   - "round_tf32": store the result rounded (RNA) to TF32 because its consumer is a tensor-core operand
+ *     (tcgen05 kind::tf32 would otherwise truncate).
+ */
+#ifndef MDGAN_B200_H
+#define MDGAN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDGAN_ERR_BAD_ARG (-1)
+#define MDGAN_ERR_UNSUPPORTED (-2)
+#define MDGAN_ERR_DRIVER (-3)
+
+#define MDGAN_MODE_DOWN 0  /* k4 s2 p1 gather: Conv2d forward, ConvTranspose2d data-grad   */
+#define MDGAN_MODE_UP 1    /* 4 output phases: ConvTranspose2d forward, Conv2d data-grad   */
+#define MDGAN_MODE_DENSE 2 /* plain GEMM: ConvTranspose2d(k,s1,p0) on a 1x1 input          */
+
+#define MDGAN_ACT_NONE 0
+#define MDGAN_ACT_RELU 1
+#define MDGAN_ACT_LRELU 2
+
+int mdgan_abi_version(void);
+/* 0 iff the current CUDA device is compute capability 10.x (the library only contains sm_100a code). */
+int mdgan_check_device(void);
+
+/* ---- weight packing (once per optimiser step) --------------------------------------------------------------
+ * Repack a PyTorch-layout conv weight into the K-major operand of mdgan_conv_gemm, rounded to TF32.
+ *   mode DOWN : W [N][C][4][4]  -> out [N_pad][16*C_pad]           (Conv2d.weight, or ConvTranspose2d.weight for dgrad)
+ *   mode UP   : W [C][N][4][4]  -> out [4*N_pad][4*C_pad]          (ConvTranspose2d.weight, or Conv2d.weight for dgrad)
+ *   mode DENSE: W [C][N][k][k]  -> out [KK*N][C_pad]               (first generator layer)
+ * Replaces: the implicit weight access of nn.Conv2d / nn.ConvTranspose2d in CIFAR10.py:83-98,116-133,
+ * CelebA.py:78-93,113-131. */
+int mdgan_pack_weights(const float* W, float* out, int mode, int N, int C, int N_pad, int C_pad, int KK, void* stream);
+
+/* ---- implicit-GEMM convolution, tcgen05 (kind::tf32) + TMEM + TMA ---------------------------------------------
+ * src  NHWC [n_img][Hs][Ws][C] (C % 32 == 0), wpacked from mdgan_pack_weights, rows = the low-resolution grid
+ * (n_img, Hg, Wg).  Output: DOWN/DENSE -> [n_img][Hg][Wg][N]; UP -> [n_img][2Hg][2Wg][N]; NHWC, or NCHW when
+ * out_nchw = 1 (image-side outputs).  bias (optional, [N]) is added, act = 1 applies tanh.  force_bn = 0 lets the
+ * launcher pick the tile width.
+ * Replaces: nn.Conv2d(k4,s2,p1) forward CIFAR10.py:88,92 / CelebA.py:81,85,88; nn.ConvTranspose2d forward
+ * CIFAR10.py:118-130 / CelebA.py:113-131 (+ torch.tanh CIFAR10.py:131 / CelebA.py:140); and their data
+ * gradients computed by loss.backward() (actors/worker.py:204,227) and torch.autograd.grad (actors/server.py:286). */
+int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img, int Hg, int Wg,
+                    int Hs, int Ws, int C, int mode, int N, int N_pad, int out_nchw, int act, int round_tf32,
+                    int force_bn, void* stream);
+
+/* ---- weight gradient, tcgen05 (kind::tf32, MN-major operands), split-K over pixels ----------------------------
+ * partial[split][tap][C1][C2] = sum_p lo[p][c1] * hi[gather(p, tap)][c2]; mode DOWN = 16 taps of the k4 s2 p1
+ * stencil (lo [n][Hl][Wl][C1], hi [n][2Hl][2Wl][C2]); mode DENSE = 1 tap, identity gather.  C1 % 128 == 0,
+ * C2 % 64 == 0.  mdgan_wgrad_splits gives the slice count to allocate; mdgan_wgrad_unpack reduces the slices in
+ * a fixed order and writes the PyTorch-layout gradient ([C1][C2][4][4], or [C1][N][KK] for DENSE, c1 < C1 real).
+ * Replaces: the weight gradients of loss.backward() (actors/worker.py:204) and torch.autograd.grad
+ * (actors/server.py:286-292). */
+int mdgan_wgrad_splits(int n_img, int Hl, int Wl, int C1, int C2, int mode);
+int mdgan_wgrad_gemm(const float* lo, const float* hi, float* partial, int n_img, int Hl, int Wl, int C1, int C2,
+                     int mode, int splits, void* stream);
+int mdgan_wgrad_unpack(const float* partial, float* grad, int mode, int splits, int C1, int C1p, int C2, int N, int KK,
+                       void* stream);
+int mdgan_reduce_slices(const float* partial, float* out, int slices, long long n, void* stream);
+void mdgan_debug_set_wgrad_desc(int lbo_bytes, int sbo_bytes);
+
+/* ---- image-side ("thin", 1 or 3 channel) layers on CUDA cores -------------------------------------------------
+ * mdgan_thin_down : img NCHW [n][CI][Hi][Wi], W [N][CI][4][4] -> out NHWC [n][Hi/2][Wi/2][N] (+ LeakyReLU).
+ *   Replaces nn.Conv2d(3,64,4,2,1)+LeakyReLU CIFAR10.py:85-86 / CelebA.py:78,96 and the data gradient of the
+ *   last ConvTranspose2d (CIFAR10.py:130, CelebA.py:131).
+ * mdgan_thin_wgrad: feat NHWC [n][Hl][Wl][C1], img NCHW [n][CI][2Hl][2Wl] -> partial [slices][C1][CI*16];
+ *   reduce with mdgan_reduce_slices.  Weight gradient of those two layers. */
+int mdgan_thin_down(const float* img, const float* W, float* out, int n_img, int CI, int Hi, int Wi, int N, int act,
+                    float slope, int round_tf32, void* stream);
+int mdgan_thin_wgrad_slices(int n_img, int Hl, int Wl);
+int mdgan_thin_wgrad(const float* feat, const float* img, float* partial, int n_img, int CI, int Hl, int Wl, int C1,
+                     void* stream);
+
+/* ---- train-mode BatchNorm2d fused with the following activation -----------------------------------------------
+ * x [G*Pg][C]: G independent passes (e.g. real || X_d) of Pg = b*H*W rows; statistics per pass, running stats
+ * updated once per pass in order (momentum, unbiased variance), *num_batches_tracked (int64) += G.
+ * stats [G][4][C] = mean, invstd, scale, shift (kept for backward).  workspace: mdgan_bn_workspace_floats floats.
+ * Replaces nn.BatchNorm2d + ReLU/LeakyReLU CIFAR10.py:89-94,119-128 / CelebA.py:97-99,134-137 and their backward. */
+long long mdgan_bn_workspace_floats(int G, int Pg, int C);
+int mdgan_bn_forward(const float* x, float* out, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, long long* num_batches_tracked, float* stats, float* workspace, int G, int Pg,
+                     int C, float eps, float momentum, int act, float slope, int round_tf32, void* stream);
+int mdgan_bn_backward(const float* da, const float* x, const float* stats, float* dx, float* dgamma, float* dbeta,
+                      float* sums, float* workspace, int G, int Pg, int C, int act, float slope, int round_tf32,
+                      void* stream);
+int mdgan_act_backward(const float* da, const float* a, float* dz, long long n, int act, float slope, int round_tf32,
+                       void* stream);
+/* out = s * (1 - x^2) * scale: backward of the generator's tanh on the group-summed feedback, with the
+ * 1/(b*N) of actors/server.py:268 folded in. */
+int mdgan_tanh_backward(const float* s, const float* x, float* out, long long n, float scale, void* stream);
+
+/* ---- discriminator head: Conv2d(C,1,k,1,0) on a kxk map + Sigmoid + BCELoss -----------------------------------
+ * a NHWC [G*b][HW][C], w PyTorch [1][C][k][k], label[g] in {0,1}.  prob/loss_terms/dlogit are [G*b];
+ * loss[g] = mean BCE of pass g (log clamped at -100), loss[G] = sum over passes.  dlogit already contains 1/b and
+ * BCELoss' max(p(1-p), 1e-12) guard.
+ * Replaces CIFAR10.py:96-97,106 / CelebA.py:91-93,100-101 and nn.BCELoss actors/worker.py:96,199-204,222-227. */
+int mdgan_head_forward(const float* a, const float* w, const float* label, float* prob, float* loss_terms,
+                       float* dlogit, float* loss, int G, int b, int HW, int C, void* stream);
+int mdgan_head_backward(const float* a, const float* w, const float* dlogit, float* da, float* dw, int n_total, int HW,
+                        int C, void* stream);
+
+/* ---- torch.optim.Adam on a flat parameter buffer (actors/server.py:111-113,308-312; actors/worker.py:97-99,206).
+ * step_count is a device int32 holding the number of steps already taken; it is incremented on the device. */
+int mdgan_adam_step(float* p, const float* g, float* m, float* v, long long n, int* step_count, float lr, float beta1,
+                    float beta2, float eps, void* stream);
+
+/* ---- small helpers ----------------------------------------------------------------------------------------- */
+int mdgan_pad_rows(const float* in, float* out, int rows, int cols_in, int cols_out, int round_tf32, void* stream);
+/* out[i] = sum_k in[k*stride + i]: sums the feedbacks of the workers that share one generated batch
+ * (actors/server.py:271-297, collapsed by linearity of the VJP). */
+int mdgan_sum_slices(const float* in, float* out, long long n, int count, long long stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDGAN_B200_H */
