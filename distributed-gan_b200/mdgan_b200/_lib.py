@@ -20,11 +20,11 @@ _ll = C.c_longlong
 SIGNATURES = {
     "mdgan_abi_version": (_i, []),
     "mdgan_check_device": (_i, []),
-    "mdgan_conv_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mdgan_conv_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_wgrad_splits": (_i, [_i, _i, _i, _i, _i, _i]),
-    "mdgan_wgrad_gemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mdgan_wgrad_gemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_debug_set_wgrad_desc": (None, [_i, _i]),
-    "mdgan_pack_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "mdgan_pack_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_wgrad_unpack": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_reduce_slices": (_i, [_p, _p, _i, _ll, _p]),
     "mdgan_bn_workspace_floats": (_ll, [_i, _i, _i]),

@@ -15,6 +15,14 @@
 //   warps 0-7 : A producers (cp.async 16 B gathers with zero-fill for padding, manual 128B swizzle), then epilogue
 //   warp  8   : B producer (TMA 2D tiled load, SWIZZLE_128B, mbarrier complete_tx)
 //   warp  9   : TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees smem stages
+//
+// Precision modes (template X3):
+//   tf32   : one tcgen05.mma per K=8 slice; operands are fp32 words that their producers rounded to TF32.
+//   tf32x3 : error-compensated split ("3xTF32"): every operand x is held as hi = tf32(x) and lo = x - hi; the
+//            product is accumulated as lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator, which restores ~fp32
+//            accuracy (the parity mode: plain TF32 through BatchNorm + (Leaky)ReLU gates is only good to a few
+//            percent on gradients, exactly like cuDNN's TF32 path -- see DESIGN.md).  The A producers split their
+//            own cp.async'd chunks in shared memory; the weight pack kernel pre-splits B.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -32,6 +40,8 @@ struct ConvGemmParams {
   int act;            // 0: none, 1: tanh
   int M;
   int round_tf32;     // 1: store outputs rounded to TF32 (they feed another tensor-core operand)
+  int accumulate;     // 1: dst += result (NCHW outputs only; sums feedbacks of workers sharing a batch)
+  int lo_row_offset;  // tf32x3: row offset of the `lo` half of the packed weights
 };
 
 constexpr int kBM = 128;
@@ -39,14 +49,22 @@ constexpr int kBK = 32;  // fp32 elements per K step = 128 bytes
 constexpr int kNumProducerWarps = 8;
 constexpr int kThreads = (kNumProducerWarps + 2) * 32;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool X3>
 struct ConvGemmSmem {
   static constexpr int kABytes = kBM * 128;
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kHalfBytes = kABytes + kBBytes;             // [A_hi | B_hi] then (X3) [A_lo | B_lo]
+  static constexpr int kStageBytes = (X3 ? 2 : 1) * kHalfBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
+  // tf32x3 keeps several TMEM accumulators: the tensor core adds into its fp32 accumulator with truncation, so a
+  // long accumulation chain drifts by ~4e-8 per add (measured: 1.5e-5 at K = 4096 with one accumulator).  The
+  // hi*hi products are dealt round-robin over kMain accumulators, the two small correction products go to their
+  // own accumulator, and the epilogue sums them with ordinary (round-to-nearest) fp32 adds.
+  static constexpr int kAccs = X3 ? (512 / BN > 16 ? 16 : 512 / BN) : 1;
+  static constexpr int kMain = X3 ? kAccs - 1 : 1;
+  static constexpr uint32_t kTmemCols = X3 ? (kAccs * BN < 32 ? 32 : kAccs * BN) : (BN < 32 ? 32 : BN);
 };
 
 __device__ __forceinline__ float round_to_tf32(float x) {
@@ -55,10 +73,24 @@ __device__ __forceinline__ float round_to_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <int BN, int STAGES>
+// In-place split of one 16-byte chunk: smem[hi_addr] <- hi = tf32(x), smem[hi_addr + lo_delta] <- lo = tf32(x - hi).
+__device__ __forceinline__ void split_chunk_x3(uint32_t hi_addr, uint32_t lo_delta) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi_addr));
+  // hi = x rounded to nearest TF32 (so the tensor core's truncation of hi is exact and the split is unbiased);
+  // lo = (x - hi) rounded to nearest TF32.  |lo| <= 2^-11 |x|, and the dropped lo*lo term is ~2^-22 relative.
+  float4 h, l;
+  h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+  l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr + lo_delta), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
+               : "memory");
+}
+
+template <int BN, int STAGES, bool X3>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParams p) {
-  using S = ConvGemmSmem<BN, STAGES>;
+  using S = ConvGemmSmem<BN, STAGES, X3>;
   constexpr int LAG = STAGES - 2;  // cp.async groups kept in flight per producer thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,7 +119,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
     fence_mbar_init();
   }
   if (warp == 8 && lane == 0) tma_prefetch_desc(&tmap_w);
-  if (warp == 9) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_ptr_smem);
+  if (warp == 9) tmem_alloc<S::kTmemCols>(tmem_ptr_smem);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -136,14 +168,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
       cp_async_commit();
       if (it >= LAG) {
         cp_async_wait<LAG>();
+        const int sd = (it - LAG) % STAGES;
+        if (X3) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = row_in + 32 * i;
+            split_chunk_x3(a_smem0 + sd * S::kStageBytes + r * 128 + ((chunk ^ (r & 7)) << 4), S::kHalfBytes);
+          }
+        }
         fence_proxy_async_smem();
-        mbar_arrive(&full_bar[(it - LAG) % STAGES]);
+        mbar_arrive(&full_bar[sd]);
       }
       if (++cc == cchunks) { cc = 0; ++tap; }
     }
     cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int it = (ksteps > LAG ? ksteps - LAG : 0); it < ksteps; ++it) mbar_arrive(&full_bar[it % STAGES]);
+    for (int it = (ksteps > LAG ? ksteps - LAG : 0); it < ksteps; ++it) {
+      const int sd = it % STAGES;
+      if (X3) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = row_in + 32 * i;
+          split_chunk_x3(a_smem0 + sd * S::kStageBytes + r * 128 + ((chunk ^ (r & 7)) << 4), S::kHalfBytes);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&full_bar[sd]);
+    }
 
     // ------------------------------------------------------------------ epilogue
     mbar_wait(tmem_full_bar, 0);
@@ -167,6 +217,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
         const int col = half * kColsPerHalf + c16;
         float v[16];
         tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
+        if (X3) {
+          const int valid = ksteps * (kBK / 8) < S::kMain ? ksteps * (kBK / 8) : S::kMain;
+          float t[16];
+          for (int a = 1; a < valid; ++a) {
+            tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col, t);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += t[j];
+          }
+          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + S::kMain * BN + col, t);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += t[j];
+        }
         if (!ok) continue;
         const int nbase = n0 + col;
 #pragma unroll
@@ -191,8 +253,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (nbase + j < p.N)
-              p.dst[(static_cast<size_t>(img * p.N + nbase + j) * Ho + oh) * Wo + ow] = v[j];
+            if (nbase + j < p.N) {
+              float* o = p.dst + (static_cast<size_t>(img * p.N + nbase + j) * Ho + oh) * Wo + ow;
+              *o = p.accumulate ? (*o + v[j]) : v[j];
+            }
         }
       }
     }
@@ -205,8 +269,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
         const int s = it % STAGES;
         const uint32_t par = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], par ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], S::kBBytes);
-        tma_load_2d(smem_u32(smem + s * S::kStageBytes + S::kABytes), &tmap_w, &full_bar[s], it * kBK, row0);
+        mbar_arrive_expect_tx(&full_bar[s], (X3 ? 2 : 1) * S::kBBytes);
+        const uint32_t b_dst = smem_u32(smem + s * S::kStageBytes + S::kABytes);
+        tma_load_2d(b_dst, &tmap_w, &full_bar[s], it * kBK, row0);
+        if (X3) tma_load_2d(b_dst + S::kHalfBytes, &tmap_w, &full_bar[s], it * kBK, row0 + p.lo_row_offset);
       }
     }
   } else {
@@ -224,7 +290,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
         for (int k = 0; k < kBK / 8; ++k) {
           const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_tf32(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          if (X3) {
+            const uint64_t da_lo = make_smem_desc_sw128(a_addr + S::kHalfBytes + k * 32, 16, 1024);
+            const uint64_t db_lo = make_smem_desc_sw128(b_addr + S::kHalfBytes + k * 32, 16, 1024);
+            const int g = it * (kBK / 8) + k;  // global K-slice counter
+            const uint32_t acc_corr = tmem_base + S::kMain * BN;
+            umma_tf32(acc_corr, da_lo, db, idesc, g != 0 ? 1u : 0u);
+            umma_tf32(acc_corr, da, db_lo, idesc, 1u);
+            umma_tf32(tmem_base + (g % S::kMain) * BN, da, db, idesc, g >= S::kMain ? 1u : 0u);
+          } else {
+            umma_tf32(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);
       }
@@ -234,20 +310,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
   __syncthreads();
   if (warp == 9) {
     tc_fence_after_sync();
-    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+    tmem_dealloc<S::kTmemCols>(tmem_base);
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool X3>
 static int launch_conv_gemm(const CUtensorMap& tmap, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
-  using S = ConvGemmSmem<BN, STAGES>;
+  using S = ConvGemmSmem<BN, STAGES, X3>;
   static bool configured = false;
   if (!configured) {
-    MDGAN_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MDGAN_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     S::kDynamic));
     configured = true;
   }
-  conv_gemm_kernel<BN, STAGES><<<grid, kThreads, S::kDynamic, st>>>(tmap, p);
+  conv_gemm_kernel<BN, STAGES, X3><<<grid, kThreads, S::kDynamic, st>>>(tmap, p);
   MDGAN_CHECK_LAUNCH();
   return 0;
 }
@@ -259,7 +335,7 @@ using namespace mdgan;
 // See include/mdgan_b200.h for the contract.
 extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img,
                                int Hg, int Wg, int Hs, int Ws, int C, int mode, int N, int N_pad, int out_nchw,
-                               int act, int round_tf32, int force_bn, void* stream) {
+                               int act, int round_tf32, int accumulate, int precision, int force_bn, void* stream) {
   if (!src || !wpacked || !dst) return MDGAN_ERR_BAD_ARG;
   if (C <= 0 || C % kBK != 0 || mode < 0 || mode > 2) return MDGAN_ERR_UNSUPPORTED;
   if (N_pad % 16 != 0 || N > N_pad || N <= 0) return MDGAN_ERR_UNSUPPORTED;
@@ -269,6 +345,8 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   p.mode = mode; p.N = N; p.N_pad = N_pad; p.out_nchw = out_nchw; p.act = act;
   p.M = n_img * Hg * Wg;
   p.round_tf32 = round_tf32;
+  p.accumulate = accumulate;
+  if (accumulate && !out_nchw) return MDGAN_ERR_UNSUPPORTED;
   if (p.M <= 0) return MDGAN_ERR_BAD_ARG;
   const int taps = mode == 0 ? 16 : (mode == 1 ? 4 : 1);
   const int phases = mode == 1 ? 4 : 1;
@@ -278,20 +356,25 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   for (int c : {128, 64, 32})
     if (N_pad % c == 0) { bn = c; break; }
   while (bn > 32 && row_tiles * phases * (N_pad / bn) < 148 && N_pad % (bn / 2) == 0) bn /= 2;
+  if (precision == 1 && bn > 64) bn = 64;  // tf32x3: leave TMEM room for >= 7 main accumulators
   if (force_bn > 0) {
-    if (N_pad % force_bn != 0) return MDGAN_ERR_BAD_ARG;
+    if (N_pad % force_bn != 0 || (precision == 1 && force_bn > 64)) return MDGAN_ERR_BAD_ARG;
     bn = force_bn;
   }
+  if (precision != 0 && precision != 1) return MDGAN_ERR_BAD_ARG;
+  const bool x3 = precision == 1;
+  const uint64_t rows = static_cast<uint64_t>(N_pad) * phases;
+  p.lo_row_offset = static_cast<int>(rows);
   CUtensorMap tmap;
-  int rc = get_tmap_2d_f32(wpacked, static_cast<uint64_t>(N_pad) * phases, static_cast<uint64_t>(taps) * C, bn, &tmap);
+  int rc = get_tmap_2d_f32(wpacked, rows * (x3 ? 2 : 1), static_cast<uint64_t>(taps) * C, bn, &tmap);
   if (rc != 0) return rc;
   dim3 grid(row_tiles, N_pad / bn, phases);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 128: return launch_conv_gemm<128, 6>(tmap, p, grid, st);
-    case 64: return launch_conv_gemm<64, 4>(tmap, p, grid, st);
-    case 32: return launch_conv_gemm<32, 4>(tmap, p, grid, st);
-    case 16: return launch_conv_gemm<16, 4>(tmap, p, grid, st);
+    case 128: return x3 ? MDGAN_ERR_UNSUPPORTED : launch_conv_gemm<128, 6, false>(tmap, p, grid, st);
+    case 64: return x3 ? launch_conv_gemm<64, 4, true>(tmap, p, grid, st) : launch_conv_gemm<64, 4, false>(tmap, p, grid, st);
+    case 32: return x3 ? launch_conv_gemm<32, 4, true>(tmap, p, grid, st) : launch_conv_gemm<32, 4, false>(tmap, p, grid, st);
+    case 16: return x3 ? launch_conv_gemm<16, 4, true>(tmap, p, grid, st) : launch_conv_gemm<16, 4, false>(tmap, p, grid, st);
     default: return MDGAN_ERR_UNSUPPORTED;
   }
 }

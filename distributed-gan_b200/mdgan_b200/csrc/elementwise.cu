@@ -19,8 +19,9 @@ __device__ __forceinline__ float to_tf32(float x) {
 // mode 1 (UP):    out[ph][n][t][c]    = W[c][n][kh][kw]              W: [C][N][4][4], kh=(1-ph_h)+2a, kw=(1-ph_w)+2b
 // mode 2 (DENSE): out[kk*N + n][c]    = W[c][n][kk]                  W: [C][N][KK]    (convT on a 1x1 input)
 // Rows n >= N and columns c >= C are zero padding (N_pad rows per phase / C_pad columns per tap).
+// split = 1 (tf32x3): out holds two matrices back to back, hi = tf32(w) and lo = tf32(w - hi).
 __global__ void pack_weights_kernel(const float* __restrict__ W, float* __restrict__ out, int mode, int N, int C,
-                                    int N_pad, int C_pad, int KK, long long total) {
+                                    int N_pad, int C_pad, int KK, long long total, int split) {
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
   float v = 0.f;
@@ -44,7 +45,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, float* __restri
     const int kk = row / N;
     if (c < C) v = W[((long long)c * N + n) * KK + kk];
   }
-  out[idx] = to_tf32(v);
+  const float hi = to_tf32(v);
+  out[idx] = hi;
+  if (split) out[total + idx] = to_tf32(v - hi);
 }
 
 // Reduce split-K partial slices and scatter to the PyTorch parameter layout.
@@ -385,7 +388,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ a, const float* __rest
 }
 
 // ----------------------------------------------------------------------------------------------- Adam (torch.optim.Adam)
-// step_count lives on the device so the launch is CUDA-graph friendly; it is incremented by block 0.
+// step_count lives on the device so the launch is CUDA-graph friendly; adam_tick_kernel increments it afterwards.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, int* __restrict__ step_count, float lr, float beta1,
                             float beta2, float eps) {
@@ -441,14 +444,14 @@ using namespace mdgan;
 static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 extern "C" int mdgan_pack_weights(const float* W, float* out, int mode, int N, int C, int N_pad, int C_pad, int KK,
-                                  void* stream) {
+                                  int split, void* stream) {
   if (!W || !out || mode < 0 || mode > 2) return MDGAN_ERR_BAD_ARG;
   long long total;
   if (mode == 0) total = (long long)N_pad * 16 * C_pad;
   else if (mode == 1) total = 4LL * N_pad * 4 * C_pad;
   else total = (long long)KK * N * C_pad;
   pack_weights_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(W, out, mode, N, C, N_pad, C_pad, KK,
-                                                                                total);
+                                                                                total, split);
   MDGAN_CHECK_LAUNCH();
   return 0;
 }

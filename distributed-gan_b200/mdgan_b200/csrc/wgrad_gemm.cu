@@ -41,19 +41,39 @@ __device__ __forceinline__ uint32_t swz32(int c16, int r) {
   return static_cast<uint32_t>(((((c16 >> 1) ^ (r & 3)) << 5) | ((c16 & 1) << 4)));
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool X3>
 struct WgradSmem {
   static constexpr int kABytes = (kWM / 32) * kWK * 128;
   static constexpr int kBBytes = (BN / 32) * kWK * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kHalfBytes = kABytes + kBBytes;  // [A_hi | B_hi] then (tf32x3) [A_lo | B_lo]
+  static constexpr int kStageBytes = (X3 ? 2 : 1) * kHalfBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;
+  // tf32x3: several TMEM accumulators to keep the truncating in-tensor-core accumulation chains short
+  // (see conv_gemm.cu); kMain round-robin accumulators for hi*hi plus one for the correction products.
+  static constexpr int kAccs = X3 ? (512 / BN > 16 ? 16 : 512 / BN) : 1;
+  static constexpr int kMain = X3 ? kAccs - 1 : 1;
+  static constexpr uint32_t kTmemCols = X3 ? kAccs * BN : BN;
 };
 
-template <int BN, int STAGES>
+// tf32x3 split of one 16-byte chunk in place (see conv_gemm.cu): hi stays, the remainder goes to +lo_delta.
+__device__ __forceinline__ void wsplit_chunk_x3(uint32_t hi_addr, uint32_t lo_delta) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi_addr));
+  // hi = x rounded to nearest TF32 (so the tensor core's truncation of hi is exact and the split is unbiased);
+  // lo = (x - hi) rounded to nearest TF32.  |lo| <= 2^-11 |x|, and the dropped lo*lo term is ~2^-22 relative.
+  float4 h, l;
+  h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+  l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr + lo_delta), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
+               : "memory");
+}
+
+template <int BN, int STAGES, bool X3>
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradParams p) {
-  using S = WgradSmem<BN, STAGES>;
+  using S = WgradSmem<BN, STAGES, X3>;
   constexpr int LAG = STAGES - 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -83,7 +103,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
     mbar_init(tmem_full_bar, 1);
     fence_mbar_init();
   }
-  if (warp == kWProducerWarps) tmem_alloc<BN>(tmem_ptr_smem);
+  if (warp == kWProducerWarps) tmem_alloc<S::kTmemCols>(tmem_ptr_smem);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -102,6 +122,21 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
     const int b_cidx = threadIdx.x % kBChunksPerRow;
     const int b_row0 = threadIdx.x / kBChunksPerRow;
     const int hw_l = p.Hl * p.Wl;
+    // tf32x3: every thread splits exactly the chunks it copied itself (visible to it after cp.async.wait_group)
+    auto split_stage = [&](int sd) {
+      const uint32_t a_stage = smem0 + sd * S::kStageBytes;
+      const uint32_t b_stage = a_stage + S::kABytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = a_row0 + 8 * i;
+        wsplit_chunk_x3(a_stage + (a_cidx >> 3) * (kWK * 128) + r * 128 + swz32(a_cidx & 7, r), S::kHalfBytes);
+      }
+#pragma unroll
+      for (int i = 0; i < kBPasses; ++i) {
+        const int r = b_row0 + kBRowsPerPass * i;
+        wsplit_chunk_x3(b_stage + (b_cidx >> 3) * (kWK * 128) + r * 128 + swz32(b_cidx & 7, r), S::kHalfBytes);
+      }
+    };
     for (int it = 0; it < ksteps; ++it) {
       const int s = it % STAGES;
       const uint32_t par = (it / STAGES) & 1;
@@ -139,13 +174,19 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
       cp_async_commit();
       if (it >= LAG) {
         cp_async_wait<LAG>();
+        const int sd = (it - LAG) % STAGES;
+        if (X3) split_stage(sd);
         fence_proxy_async_smem();
-        mbar_arrive(&full_bar[(it - LAG) % STAGES]);
+        mbar_arrive(&full_bar[sd]);
       }
     }
     cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int it = (ksteps > LAG ? ksteps - LAG : 0); it < ksteps; ++it) mbar_arrive(&full_bar[it % STAGES]);
+    for (int it = (ksteps > LAG ? ksteps - LAG : 0); it < ksteps; ++it) {
+      const int sd = it % STAGES;
+      if (X3) split_stage(sd);
+      fence_proxy_async_smem();
+      mbar_arrive(&full_bar[sd]);
+    }
 
     // ---------------------------------------------------------------- epilogue: TMEM -> partial[split][tap]
     if (ksteps > 0) {
@@ -163,6 +204,18 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
       float v[16];
       if (ksteps > 0) {
         tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
+        if (X3) {
+          const int valid = ksteps * (kWK / 8) < S::kMain ? ksteps * (kWK / 8) : S::kMain;
+          float t[16];
+          for (int a = 1; a < valid; ++a) {
+            tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col, t);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += t[j];
+          }
+          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + S::kMain * BN + col, t);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += t[j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -189,7 +242,17 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
         for (int k = 0; k < kWK / 8; ++k) {
           const uint64_t da = make_smem_desc_sw128(a_addr + k * 1024, p.lbo_a, p.sbo_a, 1);
           const uint64_t db = make_smem_desc_sw128(b_addr + k * 1024, p.lbo_b, p.sbo_b, 1);
-          umma_tf32(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          if (X3) {
+            const uint64_t da_lo = make_smem_desc_sw128(a_addr + S::kHalfBytes + k * 1024, p.lbo_a, p.sbo_a, 1);
+            const uint64_t db_lo = make_smem_desc_sw128(b_addr + S::kHalfBytes + k * 1024, p.lbo_b, p.sbo_b, 1);
+            const int g = it * (kWK / 8) + k;
+            const uint32_t acc_corr = tmem_base + S::kMain * BN;
+            umma_tf32(acc_corr, da_lo, db, idesc, g != 0 ? 1u : 0u);
+            umma_tf32(acc_corr, da, db_lo, idesc, 1u);
+            umma_tf32(tmem_base + (g % S::kMain) * BN, da, db, idesc, g >= S::kMain ? 1u : 0u);
+          } else {
+            umma_tf32(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);
       }
@@ -199,20 +262,20 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
   __syncthreads();
   if (warp == kWProducerWarps) {
     tc_fence_after_sync();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<S::kTmemCols>(tmem_base);
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool X3>
 static int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
-  using S = WgradSmem<BN, STAGES>;
+  using S = WgradSmem<BN, STAGES, X3>;
   static bool configured = false;
   if (!configured) {
-    MDGAN_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MDGAN_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BN, STAGES, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     S::kDynamic));
     configured = true;
   }
-  wgrad_gemm_kernel<BN, STAGES><<<grid, kWThreads, S::kDynamic, st>>>(p);
+  wgrad_gemm_kernel<BN, STAGES, X3><<<grid, kWThreads, S::kDynamic, st>>>(p);
   MDGAN_CHECK_LAUNCH();
   return 0;
 }
@@ -235,7 +298,7 @@ extern "C" void mdgan_debug_set_wgrad_desc(int lbo_bytes, int sbo_bytes) {
 extern "C" int mdgan_wgrad_splits(int n_img, int Hl, int Wl, int C1, int C2, int mode) {
   const int P = n_img * Hl * Wl;
   const int taps = mode == 0 ? 16 : 1;
-  const int bn = (C2 % 128 == 0) ? 128 : 64;
+  const int bn = 64;  // conservative (the tf32x3 tile): never under-counts the slices either precision needs
   const int tiles = (C1 / kWM) * (C2 / bn) * taps;
   int splits = tiles >= 148 ? 1 : (148 + tiles - 1) / tiles;
   const int max_splits = (P + 4 * kWK - 1) / (4 * kWK);  // at least 128 pixels per split
@@ -245,7 +308,7 @@ extern "C" int mdgan_wgrad_splits(int n_img, int Hl, int Wl, int C1, int C2, int
 }
 
 extern "C" int mdgan_wgrad_gemm(const float* lo, const float* hi, float* partial, int n_img, int Hl, int Wl, int C1,
-                                int C2, int mode, int splits, void* stream) {
+                                int C2, int mode, int splits, int precision, void* stream) {
   if (!lo || !hi || !partial) return MDGAN_ERR_BAD_ARG;
   if (C1 % kWM != 0 || C2 % 64 != 0 || (mode != 0 && mode != 2) || splits < 1) return MDGAN_ERR_UNSUPPORTED;
   WgradParams p{};
@@ -260,9 +323,11 @@ extern "C" int mdgan_wgrad_gemm(const float* lo, const float* hi, float* partial
   p.lbo_a = p.lbo_b = g_dbg_lbo ? g_dbg_lbo : kWK * 128;  // distance between 32-channel groups
   p.sbo_a = p.sbo_b = g_dbg_sbo ? g_dbg_sbo : 512;        // distance between 4-pixel swizzle atoms
   const int taps = mode == 0 ? 16 : 1;
-  const int bn = (C2 % 128 == 0) ? 128 : 64;
+  const int bn = (C2 % 128 == 0 && precision == 0) ? 128 : 64;  // tf32x3: BN = 64 leaves room for 7+1 accumulators
   dim3 grid(C1 / kWM, C2 / bn, taps * splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 128) return launch_wgrad<128, 4>(p, grid, st);
-  return launch_wgrad<64, 4>(p, grid, st);
+  if (precision != 0 && precision != 1) return MDGAN_ERR_BAD_ARG;
+  if (precision == 1) return launch_wgrad<64, 4, true>(p, grid, st);
+  if (bn == 128) return launch_wgrad<128, 4, false>(p, grid, st);
+  return launch_wgrad<64, 4, false>(p, grid, st);
 }

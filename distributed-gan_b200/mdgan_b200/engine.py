@@ -1,0 +1,178 @@
+"""One GPU process of the MD-GAN training loop: the generator (process 0 only) plus the discriminator workers this
+process hosts.  Mirrors, iteration for iteration, what the reference runs as N+1 OS processes:
+
+    server loop  /root/reference/src/actors/server.py:213-333
+    worker loop  /root/reference/src/actors/worker.py:157-284
+
+Order of operations inside `iteration(epoch)` (reference order kept; the G/D synchrony of the reference is strict):
+  1. process 0: z ~ N(0,1) [k*b, z_dim] (host torch RNG in parity mode, server.py:219), X = G(z)
+  2. broadcast X                                    (C4, exchange.broadcast_fakes)
+  3. every hosted worker n: `local_epochs` x D.train_step(real_n, X[(n+1)%k]); feedback on X[n%k] accumulated
+     into slot n%k of S [k*b, C, H, W]
+  4. reduce S to process 0                          (C3, exchange.reduce_feedback)
+  5. process 0: G.backward(S, 1/(b*N)) -- ONE backward on the group-summed feedback instead of the reference's N
+     retain_graph VJPs (server.py:271-297; equal by linearity) -- then Adam (server.py:308-312)
+  6. if due: process 0 draws the swap pairs on its host RNG (server.py:321), broadcast, pairwise state exchange
+     (worker.py:252-282); Adam moments stay with the rank.
+
+The compute objects come from a factory so the host-side protocol (routing, reduce slots, swap, RNG order) can be
+exercised on gloo/CPU tensors by the tests with stand-in nets; the default factory builds the CUDA nets and there is
+no CPU product path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import routing
+from .exchange import Exchange
+
+
+@dataclass
+class EngineConfig:
+    n_workers: int
+    batch_size: int
+    z_dim: int
+    image_shape: Tuple[int, int, int]
+    generator_lr: float = 2e-4
+    discriminator_lr: float = 2e-4
+    beta_1: float = 0.5
+    beta_2: float = 0.999
+    swap_interval: int = 1
+    local_epochs: int = 1
+    z_source: str = "host"      # "host": torch CPU randn in the reference's RNG order (parity); "device": CUDA Philox
+
+
+class CudaNetFactory:
+    """Builds the sm_100a nets; raises if CUDA or the kernel library is unavailable (no fallback)."""
+
+    def __init__(self, device: torch.device):
+        if device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("the MD-GAN B200 engine needs a CUDA device (no CPU fallback); got " + str(device))
+        from . import _lib
+
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            _lib.check(lib.mdgan_check_device(), "libmdgan_b200.so is sm_100a-only; device check")
+        self.device = device
+
+    def generator(self, module: nn.Module, cfg: EngineConfig, n_samples: int):
+        from .nets import GenNet
+
+        return GenNet(module, cfg.z_dim, cfg.image_shape, n_samples, self.device, cfg.generator_lr, cfg.beta_1, cfg.beta_2)
+
+    def discriminator(self, module: nn.Module, cfg: EngineConfig):
+        from .nets import DiscNet
+
+        return DiscNet(module, cfg.image_shape, cfg.batch_size, self.device, cfg.discriminator_lr, cfg.beta_1, cfg.beta_2)
+
+
+class MDGANEngine:
+    def __init__(self, cfg: EngineConfig, proc: int, n_procs: int, device: torch.device,
+                 generator: Optional[nn.Module], discriminators: Dict[int, nn.Module],
+                 real_sources: Dict[int, Callable[[], torch.Tensor]], factory=None, exchange: Optional[Exchange] = None):
+        """discriminators / real_sources are keyed by 0-based worker index and must cover exactly the workers
+        routing.workers_of_process(proc, n_procs, N) hosts; real_sources[n]() returns the next real batch on `device`."""
+        self.cfg, self.proc, self.n_procs, self.device = cfg, proc, n_procs, device
+        self.N = cfg.n_workers
+        self.k = routing.num_generated_batches(self.N)
+        self.b = cfg.batch_size
+        self.local = routing.workers_of_process(proc, n_procs, self.N)
+        if sorted(discriminators) != self.local or sorted(real_sources) != self.local:
+            raise ValueError(f"process {proc} must host workers {self.local}, got {sorted(discriminators)}")
+        if (generator is not None) != (proc == 0):
+            raise ValueError("the generator lives on process 0 only")
+        self.factory = factory or CudaNetFactory(device)
+        self.exchange = exchange or Exchange(proc, n_procs, self.N)
+        kb = self.k * self.b
+        self.gen = self.factory.generator(generator, cfg, kb) if proc == 0 else None
+        self.disc = {n: self.factory.discriminator(discriminators[n], cfg) for n in self.local}
+        self.real_sources = real_sources
+        self.gen_module = generator
+        self.disc_modules = discriminators
+        f = dict(device=device, dtype=torch.float32)
+        self.X = torch.zeros((kb, *cfg.image_shape), **f)
+        self.S = torch.zeros((kb, *cfg.image_shape), **f)
+        self.z = torch.zeros((kb, cfg.z_dim), **f)
+        self.z_host = torch.zeros((kb, cfg.z_dim), dtype=torch.float32,
+                                  pin_memory=(device.type == "cuda"))
+        self.d_loss = torch.zeros((len(self.local), max(cfg.local_epochs, 1)), **f)
+        self.g_loss = torch.zeros((len(self.local),), **f)
+        self.last_pairs: Optional[torch.Tensor] = None
+        self.iterations_done = 0
+
+    # ------------------------------------------------------------------------------------------ phases
+    def draw_noise(self) -> None:
+        """server.py:219 -- consumes process 0's global torch RNG exactly like the reference in parity mode."""
+        kb = self.k * self.b
+        if self.cfg.z_source == "host":
+            self.z_host.copy_(torch.randn((kb, self.cfg.z_dim, 1, 1)).view(kb, self.cfg.z_dim))
+            self.z.copy_(self.z_host, non_blocking=True)
+        else:
+            self.z.normal_()
+
+    def generate(self) -> None:
+        if self.proc == 0:
+            self.draw_noise()
+            X = self.gen.forward(self.z)
+            if X.data_ptr() != self.X.data_ptr():
+                self.X = X  # the net owns the [k*b, C, H, W] output buffer; broadcast straight out of it
+        self.exchange.broadcast_fakes(self.X)
+
+    def train_workers(self) -> None:
+        k, b = self.k, self.b
+        self.S.zero_()
+        for i, n in enumerate(self.local):
+            ig, id_ = routing.route(n, k)
+            x_g, x_d = self.X[ig * b:(ig + 1) * b], self.X[id_ * b:(id_ + 1) * b]
+            real = self.real_sources[n]()
+            net = self.disc[n]
+            for l in range(self.cfg.local_epochs):
+                self.d_loss[i, l].copy_(net.train_step(real, x_d))
+            slot = routing.feedback_slot(n, k)
+            self.g_loss[i].copy_(net.feedback_step(x_g, out=self.S[slot * b:(slot + 1) * b], accumulate=True))
+        self.exchange.reduce_feedback(self.S)
+
+    def update_generator(self) -> None:
+        if self.proc == 0:
+            self.gen.backward(self.S, 1.0 / (self.b * self.N))
+            self.gen.adam()
+
+    def maybe_swap(self, epoch: int) -> Optional[torch.Tensor]:
+        if not routing.swap_due(epoch, self.cfg.swap_interval, self.N):
+            self.last_pairs = None
+            return None
+        pairs = routing.draw_swap_pairs(self.N) if self.proc == 0 else None
+        pairs = self.exchange.broadcast_pairs(pairs, self.device)
+        states = {n: (self.disc[n].state.state_f32, self.disc[n].state.state_i64) for n in self.local}
+        for n in self.exchange.swap_states(states, pairs):
+            self.disc[n].repack()
+        self.last_pairs = pairs
+        return pairs
+
+    def iteration(self, epoch: int) -> None:
+        self.generate()
+        self.train_workers()
+        self.update_generator()
+        self.maybe_swap(epoch)
+        self.iterations_done += 1
+
+    # ------------------------------------------------------------------------------------------ results
+    def mean_d_loss(self) -> List[float]:
+        """worker.py:215 -- per hosted worker, mean over the local epochs (synchronises)."""
+        return self.d_loss[:, : self.cfg.local_epochs].mean(dim=1).tolist()
+
+    def swap_partner(self, n: int) -> Optional[int]:
+        if self.last_pairs is None:
+            return None
+        return routing.partners_from_pairs(self.last_pairs)[n + 1]
+
+    def sync_modules(self) -> None:
+        """Write the device state back into the caller's nn.Modules (before torch.save / at the end)."""
+        if self.gen is not None:
+            self.gen.state.store_to(self.gen_module)
+        for n in self.local:
+            self.disc[n].state.store_to(self.disc_modules[n])

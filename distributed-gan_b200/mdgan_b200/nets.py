@@ -1,0 +1,361 @@
+"""Device-resident generator / discriminator engines built on the C-ABI kernels.
+
+`DiscNet` executes what a reference worker does with its `nn.Module` discriminator
+(/root/reference/src/actors/worker.py:193-233): the D training step on (real, X_d) with Adam, and the error
+feedback dBCE(D(X_g),1)/dX_g.  `GenNet` executes the server's generator work
+(/root/reference/src/actors/server.py:219-223,266-312): forward over the k*b noise batch, one backward on the
+group-summed feedback (equal to the reference's N retain_graph VJPs by linearity), Adam.
+
+Data layout in HBM (per net):
+  state_f32  : [ parameters in module.parameters() order | BatchNorm running_mean/var in buffers() order ]  fp32,
+               PyTorch tensor layouts, one contiguous allocation (so the discriminator swap is one send/recv);
+  state_i64  : BatchNorm num_batches_tracked counters;
+  grad, m, v : flat fp32 mirrors of the parameter prefix (Adam is a single launch over it);
+  packed weights (TF32-rounded, K-major tensor-core operands), rebuilt after every Adam step;
+  activations: NHWC fp32, pre-BN conv outputs `z`, post-activation `a`, and their gradients `da`, `dz`.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .plan import ACT_LRELU, ACT_RELU, ConvLayer, NetPlan, extract_plan
+
+_ACT_CODE = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "lrelu": ops.ACT_LRELU}
+
+
+def _pad(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+class FlatState:
+    """Flat device copy of a module's parameters + buffers (see module docstring)."""
+
+    def __init__(self, module: nn.Module, device: torch.device):
+        self.device = device
+        self.param_names = [n for n, _ in module.named_parameters()]
+        self.param_shapes = {n: tuple(p.shape) for n, p in module.named_parameters()}
+        fbuf = [(n, b) for n, b in module.named_buffers() if b.dtype == torch.float32]
+        ibuf = [(n, b) for n, b in module.named_buffers() if b.dtype == torch.int64]
+        other = [n for n, b in module.named_buffers() if b.dtype not in (torch.float32, torch.int64)]
+        if other or any(p.dtype != torch.float32 for p in module.parameters()):
+            raise TypeError(f"only fp32 parameters and fp32/int64 buffers are supported (got {other})")
+        self.fbuf_names = [n for n, _ in fbuf]
+        self.ibuf_names = [n for n, _ in ibuf]
+        self.n_params = sum(p.numel() for p in module.parameters())
+        n_f = self.n_params + sum(b.numel() for _, b in fbuf)
+        self.state_f32 = torch.zeros(n_f, device=device, dtype=torch.float32)
+        self.state_i64 = torch.zeros(max(len(ibuf), 1), device=device, dtype=torch.int64)
+        self.params = self.state_f32[: self.n_params]
+        self.grad = torch.zeros(self.n_params, device=device, dtype=torch.float32)
+        self.m = torch.zeros_like(self.grad)
+        self.v = torch.zeros_like(self.grad)
+        self.step = torch.zeros(1, device=device, dtype=torch.int32)
+        self.p: Dict[str, torch.Tensor] = {}
+        self.g: Dict[str, torch.Tensor] = {}
+        self.b: Dict[str, torch.Tensor] = {}
+        off = 0
+        for n, prm in module.named_parameters():
+            k = prm.numel()
+            self.p[n] = self.state_f32[off: off + k].view(prm.shape)
+            self.g[n] = self.grad[off: off + k].view(prm.shape)
+            off += k
+        for n, bf in fbuf:
+            k = bf.numel()
+            self.b[n] = self.state_f32[off: off + k].view(bf.shape)
+            off += k
+        for i, (n, _) in enumerate(ibuf):
+            self.b[n] = self.state_i64[i: i + 1].view(())
+        self.load_from(module)
+
+    @torch.no_grad()
+    def load_from(self, module: nn.Module) -> None:
+        for n, prm in module.named_parameters():
+            self.p[n].copy_(prm.detach().to(self.device, non_blocking=True))
+        for n, bf in module.named_buffers():
+            self.b[n].copy_(bf.detach().to(self.device, non_blocking=True))
+
+    @torch.no_grad()
+    def store_to(self, module: nn.Module) -> None:
+        """Write the device state back into the caller's module (state_dict key order and dtypes preserved)."""
+        for n, prm in module.named_parameters():
+            prm.data.copy_(self.p[n].to(prm.device))
+        for n, bf in module.named_buffers():
+            bf.data.copy_(self.b[n].to(bf.device))
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for n in self.param_names:
+            out[n] = self.p[n].detach().cpu().clone()
+        for n in self.fbuf_names + self.ibuf_names:
+            out[n] = self.b[n].detach().cpu().clone()
+        return out
+
+
+def _cpu_copy(module: nn.Module) -> nn.Module:
+    return copy.deepcopy(module).to("cpu")
+
+
+class DiscNet:
+    def __init__(self, module: nn.Module, image_shape: Tuple[int, int, int], batch_size: int, device: torch.device,
+                 lr: float, beta_1: float, beta_2: float, max_groups: int = 2, precision: Optional[int] = None):
+        self.device, self.b, self.shape = device, batch_size, tuple(image_shape)
+        self.prec = ops.default_precision() if precision is None else precision
+        self.rnd = self.prec == ops.TF32  # single-pass TF32: producers round tensor-core operands to nearest
+        self.lr, self.beta_1, self.beta_2 = lr, beta_1, beta_2
+        self.plan: NetPlan = extract_plan(_cpu_copy(module), "discriminator", self.shape)
+        self.state = FlatState(module, device)
+        L = self.plan.layers
+        self.L = L
+        nmax = max_groups * batch_size
+        self.nmax, self.max_groups = nmax, max_groups
+        f = dict(device=device, dtype=torch.float32)
+        self.z: List[Optional[torch.Tensor]] = []
+        self.a: List[torch.Tensor] = []
+        self.da: List[torch.Tensor] = []
+        self.dz: List[torch.Tensor] = []
+        self.stats: List[Optional[torch.Tensor]] = []
+        self.sums: List[Optional[torch.Tensor]] = []
+        self.wp: List[Optional[torch.Tensor]] = []
+        self.wq: List[Optional[torch.Tensor]] = []
+        self.partial: List[Optional[torch.Tensor]] = []
+        ws = 0
+        for l, ly in enumerate(L[:-1]):
+            Ho, Cc = ly.h_out, ly.c_out
+            shape = (nmax, Ho, Ho, Cc)
+            self.z.append(torch.empty(shape, **f) if ly.bn else None)
+            self.a.append(torch.empty(shape, **f))
+            self.da.append(torch.empty(shape, **f))
+            self.dz.append(torch.empty(shape, **f))
+            self.stats.append(torch.zeros(max_groups * 4 * Cc, **f) if ly.bn else None)
+            self.sums.append(torch.zeros(max_groups * 2 * Cc, **f) if ly.bn else None)
+            if ly.bn:
+                for G in range(1, max_groups + 1):
+                    ws = max(ws, ops.bn_workspace_floats(G, batch_size * Ho * Ho, Cc))
+            # conv data-grad operand (UP): conv weight [co][ci] read as [C=co][N=ci]
+            self.wq.append(torch.empty(ops.packed_shape(ops.MODE_UP, ly.c_in, Cc, precision=self.prec), **f))
+            if l >= 1:
+                self.wp.append(torch.empty(ops.packed_shape(ops.MODE_DOWN, Cc, ly.c_in, precision=self.prec), **f))
+                splits = ops.wgrad_splits(nmax, Ho, Ho, Cc, ly.c_in, ops.MODE_DOWN)
+                self.partial.append(torch.empty(splits * 16 * Cc * ly.c_in, **f))
+            else:
+                self.wp.append(None)
+                self.partial.append(torch.empty(ops.thin_wgrad_slices(nmax, Ho, Ho) * Cc * ly.c_in * 16, **f))
+        self.bn_ws = torch.empty(max(ws, 1), **f)
+        head = L[-1]
+        self.prob = torch.zeros(nmax, **f)
+        self.loss_terms = torch.zeros(nmax, **f)
+        self.dlogit = torch.zeros(nmax, **f)
+        self.loss = torch.zeros(max_groups + 1, **f)
+        self.labels_train = torch.tensor([1.0, 0.0][:max_groups], **f)
+        self.labels_ones = torch.ones(max_groups, **f)
+        self.img = torch.empty((nmax, *self.shape), **f)          # real || X_d
+        self.feedback = torch.empty((batch_size, *self.shape), **f)
+        self.repack()
+
+    # ------------------------------------------------------------------ parameters
+    def repack(self) -> None:
+        P = self.state.p
+        for l, ly in enumerate(self.L[:-1]):
+            ops.pack_up(P[ly.weight], self.wq[l])
+            if l >= 1:
+                ops.pack_down(P[ly.weight], self.wp[l])
+
+    def adam(self) -> None:
+        s = self.state
+        ops.adam_step(s.params, s.grad, s.m, s.v, s.step, self.lr, self.beta_1, self.beta_2)
+        self.repack()
+
+    # ------------------------------------------------------------------ forward / backward
+    def forward(self, img: torch.Tensor, G: int, labels: torch.Tensor) -> None:
+        """img NCHW [G*b, C, H, W]; fills self.loss[0..G-1] (per-pass mean BCE) and self.loss[G] (their sum)."""
+        b, P, B = self.b, self.state.p, self.state.b
+        n = G * b
+        L = self.L
+        l0 = L[0]
+        ops.thin_down(img[:n], P[l0.weight], self.a[0][:n], act=ops.ACT_LRELU, slope=l0.slope, round_tf32=self.rnd)
+        for l in range(1, len(L) - 1):
+            ly = L[l]
+            Ho = ly.h_out
+            ops.conv_gemm(self.a[l - 1][:n], self.wp[l], ops.MODE_DOWN, ly.c_out, self.z[l][:n], (n, Ho, Ho),
+                          (ly.h_in, ly.h_in), bias=P[ly.bias] if ly.bias else None, precision=self.prec)
+            bn = ly.bn
+            ops.bn_forward(self.z[l][:n], self.a[l][:n], P[bn.weight], P[bn.bias], B[bn.running_mean], B[bn.running_var],
+                           B[bn.num_batches_tracked] if bn.num_batches_tracked else None, self.stats[l], self.bn_ws,
+                           G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope,
+                           round_tf32=(self.rnd and L[l + 1].kind == "down"), eps=bn.eps, momentum=bn.momentum)
+        head = L[-1]
+        ops.head_forward(self.a[-1][:n], P[head.weight], labels, self.prob, self.loss_terms, self.dlogit, self.loss, G,
+                         b, head.k * head.k, head.c_in)
+
+    def backward(self, img: torch.Tensor, G: int, train: bool, out: Optional[torch.Tensor] = None,
+                 accumulate: bool = False) -> None:
+        """train=True: parameter gradients into state.grad.  train=False: dLoss/d(img) written (or accumulated)
+        into `out` (default self.feedback), NCHW."""
+        b, P, Gd = self.b, self.state.p, self.state.g
+        n = G * b
+        L = self.L
+        head = L[-1]
+        ops.head_backward(self.a[-1][:n], P[head.weight], self.dlogit, self.da[-1][:n],
+                          Gd[head.weight] if train else None, n, head.k * head.k, head.c_in)
+        for l in range(len(L) - 2, 0, -1):
+            ly = L[l]
+            Ho, bn = ly.h_out, ly.bn
+            ops.bn_backward(self.da[l][:n], self.z[l][:n], self.stats[l], self.dz[l][:n],
+                            Gd[bn.weight] if train else None, Gd[bn.bias] if train else None, self.sums[l], self.bn_ws,
+                            G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd)
+            if train:
+                splits = ops.wgrad_splits(n, Ho, Ho, ly.c_out, ly.c_in, ops.MODE_DOWN)
+                ops.wgrad_gemm(self.dz[l][:n], self.a[l - 1][:n], self.partial[l], (n, Ho, Ho), ops.MODE_DOWN, splits,
+                               precision=self.prec)
+                ops.wgrad_unpack(self.partial[l], Gd[ly.weight], ops.MODE_DOWN, splits, ly.c_out, ly.c_out, ly.c_in)
+            ops.conv_gemm(self.dz[l][:n], self.wq[l], ops.MODE_UP, ly.c_in, self.da[l - 1][:n], (n, Ho, Ho), (Ho, Ho),
+                          precision=self.prec)
+        l0 = L[0]
+        ops.act_backward(self.da[0][:n], self.a[0][:n], self.dz[0][:n], ops.ACT_LRELU, l0.slope,
+                         round_tf32=(self.rnd and not train))
+        if train:
+            ops.thin_wgrad(self.dz[0][:n], img[:n], self.partial[0], Gd[l0.weight])
+        else:
+            ops.conv_gemm(self.dz[0][:n], self.wq[0], ops.MODE_UP, l0.c_in, self.feedback if out is None else out,
+                          (n, l0.h_out, l0.h_out), (l0.h_out, l0.h_out), out_nchw=True, accumulate=accumulate,
+                          precision=self.prec)
+
+    # ------------------------------------------------------------------ worker-level steps
+    def train_step(self, real: torch.Tensor, x_d: torch.Tensor) -> torch.Tensor:
+        """worker.py:197-206.  Returns a device view of d_loss = BCE(D(real),1) + BCE(D(X_d),0)."""
+        b = self.b
+        self.img[:b].copy_(real)
+        self.img[b: 2 * b].copy_(x_d)
+        self.forward(self.img, 2, self.labels_train)
+        self.backward(self.img, 2, train=True)
+        self.adam()
+        return self.loss[2]
+
+    def feedback_step(self, x_g: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      accumulate: bool = False) -> torch.Tensor:
+        """worker.py:220-233.  dBCE(D(X_g),1)/dX_g goes to `out` (default self.feedback; accumulate=True adds, which
+        is how feedbacks of workers sharing a generated batch are summed).  Returns the loss_gen device view."""
+        self.forward(x_g, 1, self.labels_ones)
+        self.backward(x_g, 1, train=False, out=out, accumulate=accumulate)
+        return self.loss[0]
+
+
+class GenNet:
+    def __init__(self, module: nn.Module, z_dim: int, image_shape: Tuple[int, int, int], n_samples: int,
+                 device: torch.device, lr: float, beta_1: float, beta_2: float, precision: Optional[int] = None):
+        self.device, self.n, self.z_dim, self.shape = device, n_samples, z_dim, tuple(image_shape)
+        self.prec = ops.default_precision() if precision is None else precision
+        self.rnd = self.prec == ops.TF32
+        self.lr, self.beta_1, self.beta_2 = lr, beta_1, beta_2
+        self.plan: NetPlan = extract_plan(_cpu_copy(module), "generator", (z_dim, 1, 1))
+        self.state = FlatState(module, device)
+        L = self.plan.layers
+        self.L = L
+        n = n_samples
+        f = dict(device=device, dtype=torch.float32)
+        self.zc = _pad(z_dim, 32)
+        self.zp = torch.zeros((n, self.zc), **f)
+        self.z, self.a, self.da, self.dz, self.stats, self.sums = [], [], [], [], [], []
+        self.wq: List[Optional[torch.Tensor]] = []      # forward operands (UP), l >= 1
+        self.wp_dg: List[Optional[torch.Tensor]] = []   # data-grad operands (DOWN), 1 <= l <= L-2
+        self.partial: List[Optional[torch.Tensor]] = []
+        ws = 0
+        for l, ly in enumerate(L[:-1]):
+            Ho, Cc = ly.h_out, ly.c_out
+            shape = (n, Ho, Ho, Cc)
+            self.z.append(torch.empty(shape, **f))
+            self.a.append(torch.empty(shape, **f))
+            self.da.append(torch.empty(shape, **f))
+            self.dz.append(torch.empty(shape, **f))
+            self.stats.append(torch.zeros(4 * Cc, **f))
+            self.sums.append(torch.zeros(2 * Cc, **f))
+            ws = max(ws, ops.bn_workspace_floats(1, n * Ho * Ho, Cc))
+        self.bn_ws = torch.empty(max(ws, 1), **f)
+        l0 = L[0]
+        self.kk = l0.k * l0.k
+        self.wp_dense = torch.empty(ops.packed_shape(ops.MODE_DENSE, l0.c_out, z_dim, self.kk, self.prec), **f)
+        sp0 = ops.wgrad_splits(n, 1, 1, self.zc, self.kk * l0.c_out, ops.MODE_DENSE)
+        self.partial.append(torch.empty(sp0 * self.zc * self.kk * l0.c_out, **f))
+        self.wq.append(None)
+        self.wp_dg.append(None)
+        for l in range(1, len(L)):
+            ly = L[l]
+            self.wq.append(torch.empty(ops.packed_shape(ops.MODE_UP, ly.c_out, ly.c_in, precision=self.prec), **f))
+            if l < len(L) - 1:
+                self.wp_dg.append(torch.empty(ops.packed_shape(ops.MODE_DOWN, ly.c_in, ly.c_out, precision=self.prec), **f))
+                sp = ops.wgrad_splits(n, ly.h_in, ly.h_in, ly.c_in, ly.c_out, ops.MODE_DOWN)
+                self.partial.append(torch.empty(sp * 16 * ly.c_in * ly.c_out, **f))
+            else:
+                self.wp_dg.append(None)
+                self.partial.append(torch.empty(ops.thin_wgrad_slices(n, ly.h_in, ly.h_in) * ly.c_in * ly.c_out * 16, **f))
+        self.X = torch.empty((n, *self.shape), **f)
+        self.dXt = torch.empty((n, *self.shape), **f)
+        self.repack()
+
+    def repack(self) -> None:
+        P, L = self.state.p, self.L
+        ops.pack_dense(P[L[0].weight], self.wp_dense)
+        for l in range(1, len(L)):
+            ops.pack_up(P[L[l].weight], self.wq[l])
+            if l < len(L) - 1:
+                ops.pack_down(P[L[l].weight], self.wp_dg[l])
+
+    def adam(self) -> None:
+        s = self.state
+        ops.adam_step(s.params, s.grad, s.m, s.v, s.step, self.lr, self.beta_1, self.beta_2)
+        self.repack()
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        """z [n, z_dim] (device) -> X NCHW [n, C, H, W]; train-mode BatchNorm over all n samples (server.py:219-220)."""
+        n, P, B, L = self.n, self.state.p, self.state.b, self.L
+        ops.pad_rows(z.view(n, self.z_dim), self.zp, round_tf32=self.rnd)
+        l0 = L[0]
+        ops.conv_gemm(self.zp, self.wp_dense, ops.MODE_DENSE, self.kk * l0.c_out, self.z[0], (n, 1, 1), (1, 1),
+                      precision=self.prec)
+        for l in range(len(L) - 1):
+            ly, bn = L[l], L[l].bn
+            Ho = ly.h_out
+            if l >= 1:
+                ops.conv_gemm(self.a[l - 1], self.wq[l], ops.MODE_UP, ly.c_out, self.z[l], (n, ly.h_in, ly.h_in),
+                              (ly.h_in, ly.h_in), precision=self.prec)
+            ops.bn_forward(self.z[l], self.a[l], P[bn.weight], P[bn.bias], B[bn.running_mean], B[bn.running_var],
+                           B[bn.num_batches_tracked] if bn.num_batches_tracked else None, self.stats[l], self.bn_ws,
+                           1, n * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd, eps=bn.eps,
+                           momentum=bn.momentum)
+        last = L[-1]
+        ops.conv_gemm(self.a[-1], self.wq[-1], ops.MODE_UP, last.c_out, self.X, (n, last.h_in, last.h_in),
+                      (last.h_in, last.h_in), out_nchw=True, act_tanh=True, precision=self.prec)
+        return self.X
+
+    def backward(self, s: torch.Tensor, scale: float) -> None:
+        """s NCHW [n, C, H, W]: per-sample sum of the feedbacks routed to that sample; grads = scale * J^T s."""
+        n, P, Gd, L = self.n, self.state.p, self.state.g, self.L
+        last = L[-1]
+        ops.tanh_backward(s, self.X, self.dXt, scale)
+        ops.thin_wgrad(self.a[-1], self.dXt, self.partial[-1], Gd[last.weight])
+        ops.thin_down(self.dXt, P[last.weight], self.da[-1], act=ops.ACT_NONE)
+        for l in range(len(L) - 2, -1, -1):
+            ly, bn = L[l], L[l].bn
+            Ho = ly.h_out
+            ops.bn_backward(self.da[l], self.z[l], self.stats[l], self.dz[l], Gd[bn.weight], Gd[bn.bias], self.sums[l],
+                            self.bn_ws, 1, n * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd)
+            if l >= 1:
+                hi = ly.h_in
+                splits = ops.wgrad_splits(n, hi, hi, ly.c_in, ly.c_out, ops.MODE_DOWN)
+                ops.wgrad_gemm(self.a[l - 1], self.dz[l], self.partial[l], (n, hi, hi), ops.MODE_DOWN, splits,
+                               precision=self.prec)
+                ops.wgrad_unpack(self.partial[l], Gd[ly.weight], ops.MODE_DOWN, splits, ly.c_in, ly.c_in, ly.c_out)
+                ops.conv_gemm(self.dz[l], self.wp_dg[l], ops.MODE_DOWN, ly.c_in, self.da[l - 1], (n, hi, hi), (Ho, Ho),
+                              precision=self.prec)
+            else:
+                c2 = self.kk * ly.c_out
+                splits = ops.wgrad_splits(n, 1, 1, self.zc, c2, ops.MODE_DENSE)
+                ops.wgrad_gemm(self.zp, self.dz[0].view(n, 1, 1, c2), self.partial[0], (n, 1, 1), ops.MODE_DENSE, splits,
+                               precision=self.prec)
+                ops.wgrad_unpack(self.partial[0], Gd[ly.weight], ops.MODE_DENSE, splits, self.z_dim, self.zc, c2,
+                                 N=ly.c_out, KK=self.kk)

@@ -1,0 +1,223 @@
+"""Process-level runner behind `actors.server.start` / `actors.worker.start`: rendezvous, data shards, the
+training loop, and the reference's side outputs (CSV timing logs, weight files, image grids).
+
+Outputs keep the reference's names and schemas so its notebooks keep working:
+  logs/mdgan.{N}.{dataset}.server.logs.csv          columns of /root/reference/src/actors/server.py:179-208
+  logs/mdgan.{N}.{dataset}.worker.{rank}.logs.csv   columns of /root/reference/src/actors/worker.py:129-152
+  weights/generator_{epoch}.pt, weights/generator_final.pt            (server.py:366-367,373-374)
+  weights/worker_{rank}/discriminator.pth                             (worker.py:289-292)
+  saved_images/real_images.png, saved_images/generated_epoch_{e}.png  (server.py:130-149,344-352)
+"""
+from __future__ import annotations
+
+import csv
+import logging
+import os
+import time
+from datetime import timedelta
+from pathlib import Path
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import routing
+from .engine import EngineConfig, MDGANEngine
+
+SERVER_COLUMNS = [
+    "epoch", "start.epoch", "end.epoch", "start.epoch_calculation", "end.epoch_calculation", "start.send_data",
+    "end.send_data", "start.recv_data", "end.recv_data", "start.calc_gradients", "end.calc_gradients",
+    "start.agg_gradients", "end.agg_gradients", "start.generate_data", "end.generate_data", "fid", "is", "start.fid",
+    "end.fid", "start.is", "end.is", "size.data", "size.feedback", "start.swap", "end.swap", "swap", "size.sent",
+    "size.recv",
+]
+WORKER_COLUMNS = [
+    "epoch", "start.epoch", "end.epoch", "start.calc_gradients", "end.calc_gradients", "start.recv_data",
+    "end.recv_data", "start.send", "end.send", "start.swap_recv_instruction", "end.swap_recv_instruction",
+    "start.load_state_dict", "end.load_state_dict", "start.swap_recv", "end.swap_recv", "start.swap_send",
+    "end.swap_send", "swap_with", "mean_d_loss", "size.model", "size.sent", "size.recv",
+]
+_MB = 1024 ** 2
+
+
+class _DeviceBatches:
+    """Host DataLoader (reference order) -> pinned staging -> device."""
+
+    def __init__(self, stream: routing.RealBatchStream, device: torch.device, shape):
+        self.stream, self.device = stream, device
+        self.pinned = torch.empty((stream.batch_size, *shape), dtype=torch.float32, pin_memory=True)
+        self.dev = torch.empty((stream.batch_size, *shape), dtype=torch.float32, device=device)
+
+    def __call__(self) -> torch.Tensor:
+        self.pinned.copy_(self.stream.next())
+        self.dev.copy_(self.pinned, non_blocking=True)
+        return self.dev
+
+
+def _maybe_metrics():
+    try:
+        from torchmetrics.image.fid import FrechetInceptionDistance  # noqa: F401
+        from torchmetrics.image.inception import InceptionScore  # noqa: F401
+
+        return FrechetInceptionDistance, InceptionScore
+    except Exception:
+        return None, None
+
+
+def _save_grid(images: torch.Tensor, path: Path, normalize: bool) -> None:
+    from torchvision.transforms.functional import to_pil_image
+    from torchvision.utils import make_grid
+
+    grid = make_grid(images.cpu().float(), nrow=4, normalize=normalize, value_range=(0, 1), padding=0)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    to_pil_image(grid).save(path)
+
+
+def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: torch.device, cfg: EngineConfig,
+             generator: Optional[nn.Module], discriminators: Dict[int, nn.Module], dataset, get_subset=None,
+             epochs: int, log_interval: int, log_folder: Path, dataset_name: str, iid: bool = True, n_samples: int = 5,
+             engine_hook=None) -> MDGANEngine:
+    N = routing.num_workers(world_size)
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"--device {device}: the B200 MD-GAN engine runs on CUDA only (no CPU fallback)")
+    if device.index is None:
+        device = torch.device("cuda", proc % max(torch.cuda.device_count(), 1))
+    torch.cuda.set_device(device)
+    owns_pg = False
+    if n_procs > 1 and not dist.is_initialized():
+        if backend != "nccl":
+            raise RuntimeError(f"--backend {backend}: multi-GPU runs use NCCL over NVLink (one process per GPU)")
+        dist.init_process_group(backend="nccl", rank=proc, world_size=n_procs, timeout=timedelta(weeks=52),
+                                device_id=device)
+        owns_pg = True
+        dist.barrier()
+    logging.info(f"GPU process {proc}/{n_procs} on {device}: hosts workers "
+                 f"{[n + 1 for n in routing.workers_of_process(proc, n_procs, N)]}" + (" and the server" if proc == 0 else ""))
+
+    # data shards: every process derives the same seed-0 split locally (replaces the index send of server.py:157-167)
+    shards = routing.split_dataset(len(dataset), N, iid)
+    local = routing.workers_of_process(proc, n_procs, N)
+    sources = {n: _DeviceBatches(routing.RealBatchStream(dataset, shards[n], cfg.batch_size), device, cfg.image_shape)
+               for n in local}
+    engine = MDGANEngine(cfg, proc, n_procs, device, generator, discriminators, sources)
+    if engine_hook is not None:
+        engine_hook(engine)
+
+    name = f"mdgan.{N}.{dataset_name}"
+    log_folder = Path(log_folder)
+    log_folder.mkdir(parents=True, exist_ok=True)
+    image_dir, weights_dir = Path("saved_images"), Path("weights")
+    k, b = engine.k, cfg.batch_size
+    img_bytes = 4 * b * cfg.image_shape[0] * cfg.image_shape[1] * cfg.image_shape[2]
+    server_f = server_w = None
+    if proc == 0:
+        server_f = open(log_folder / f"{name}.server.logs.csv", "a", encoding="utf-8")
+        server_w = csv.DictWriter(server_f, fieldnames=SERVER_COLUMNS)
+        server_w.writeheader()
+        g = torch.Generator()
+        g.manual_seed(0)  # server.py:130-149: constant real batch for the image grid / FID
+        real_eval = next(iter(torch.utils.data.DataLoader(dataset, batch_size=n_samples, shuffle=True, generator=g)))[0]
+        real_eval = (real_eval.repeat(1, 3, 1, 1) if real_eval.shape[1] < 3 else real_eval)
+        real_eval = (real_eval + 1) * 0.5
+        _save_grid(real_eval, image_dir / "real_images.png", normalize=True)
+    worker_files, worker_writers = {}, {}
+    model_mb = {}
+    for n in local:
+        f = open(log_folder / f"{name}.worker.{n + 1}.logs.csv", "a", encoding="utf-8")
+        w = csv.DictWriter(f, fieldnames=WORKER_COLUMNS)
+        w.writeheader()
+        worker_files[n], worker_writers[n] = f, w
+        m = discriminators[n]
+        model_mb[n] = (sum(p.nelement() * p.element_size() for p in m.parameters())
+                       + sum(bf.nelement() * bf.element_size() for bf in m.buffers())) / _MB
+
+    sync_timing = os.environ.get("MDGAN_SYNC_TIMING", "0") == "1"
+
+    def stamp() -> float:
+        if sync_timing:
+            torch.cuda.synchronize(device)
+        return time.time()
+
+    FID, IS = _maybe_metrics()
+    for epoch in range(epochs):
+        t0 = stamp()
+        srow = {c: None for c in SERVER_COLUMNS}
+        srow.update({"epoch": epoch, "start.epoch": t0, "start.epoch_calculation": t0, "swap": False,
+                     "size.data": 2 * img_bytes / _MB, "size.feedback": N * img_bytes / _MB,
+                     "size.sent": N * 2 * img_bytes / _MB, "size.recv": N * img_bytes / _MB})
+        wrows = {n: {c: None for c in WORKER_COLUMNS} for n in local}
+        for n in local:
+            wrows[n].update({"epoch": epoch, "start.epoch": t0, "size.model": model_mb[n],
+                             "size.sent": img_bytes / _MB, "size.recv": 2 * img_bytes / _MB})
+        srow["start.generate_data"] = t0
+        engine.generate()
+        t1 = stamp()
+        srow["end.generate_data"] = srow["start.send_data"] = srow["end.send_data"] = srow["start.recv_data"] = t1
+        for n in local:
+            wrows[n]["start.recv_data"], wrows[n]["end.recv_data"], wrows[n]["start.calc_gradients"] = t0, t1, t1
+        engine.train_workers()
+        t2 = stamp()
+        srow["end.recv_data"] = srow["start.agg_gradients"] = t2
+        for n in local:
+            wrows[n]["end.calc_gradients"] = wrows[n]["start.send"] = wrows[n]["end.send"] = wrows[n]["end.epoch"] = t2
+        engine.update_generator()
+        t3 = stamp()
+        srow["end.agg_gradients"] = srow["start.calc_gradients"] = srow["end.calc_gradients"] = t3
+        pairs = engine.maybe_swap(epoch)
+        engine.iterations_done += 1
+        t4 = stamp()
+        if pairs is not None:
+            srow.update({"swap": True, "start.swap": t3, "end.swap": t4})
+            for n in local:
+                wrows[n].update({"swap_with": engine.swap_partner(n), "start.swap_recv_instruction": t3,
+                                 "end.swap_recv_instruction": t3, "start.swap_send": t3, "end.swap_send": t4,
+                                 "start.swap_recv": t3, "end.swap_recv": t4, "start.load_state_dict": t4,
+                                 "end.load_state_dict": t4})
+                wrows[n]["size.sent"] += model_mb[n]
+                wrows[n]["size.recv"] += model_mb[n]
+        srow["end.epoch_calculation"] = t4
+        losses = engine.mean_d_loss()  # one small D2H per iteration, like the reference's losses.mean().item()
+        for i, n in enumerate(local):
+            wrows[n]["mean_d_loss"] = losses[i]
+            worker_writers[n].writerow(wrows[n])
+        if proc == 0:
+            if epoch % log_interval == 0 or epoch == epochs - 1:  # server.py:336-367
+                fake = engine.X.detach().cpu()
+                fake = fake.repeat(1, 3, 1, 1) if fake.shape[1] < 3 else fake
+                fake = (fake + 1) * 0.5
+                _save_grid(fake, image_dir / f"generated_epoch_{epoch}.png", normalize=False)
+                if FID is not None:
+                    ev = fake[: min(n_samples, len(fake))]
+                    srow["start.is"] = time.time()
+                    inc = IS(normalize=True, splits=1)
+                    inc.update(ev)
+                    srow["is"] = inc.compute()[0].item()
+                    srow["end.is"] = srow["start.fid"] = time.time()
+                    fid = FID(normalize=True)
+                    fid.update(ev, real=True)
+                    fid.update(real_eval, real=False)
+                    srow["fid"] = fid.compute().item()
+                    srow["end.fid"] = time.time()
+                engine.gen.state.store_to(generator)
+                weights_dir.mkdir(parents=True, exist_ok=True)
+                torch.save(generator.state_dict(), weights_dir / f"generator_{epoch}.pt")
+            srow["end.epoch"] = time.time()
+            server_w.writerow(srow)
+
+    torch.cuda.synchronize(device)
+    engine.sync_modules()
+    if proc == 0:
+        weights_dir.mkdir(parents=True, exist_ok=True)
+        torch.save(generator.state_dict(), weights_dir / "generator_final.pt")
+        server_f.close()
+    for n in local:
+        d = weights_dir / f"worker_{n + 1}"
+        d.mkdir(parents=True, exist_ok=True)
+        torch.save(discriminators[n].state_dict(), d / "discriminator.pth")
+        worker_files[n].close()
+    if owns_pg:
+        dist.barrier()
+        dist.destroy_process_group()
+    return engine

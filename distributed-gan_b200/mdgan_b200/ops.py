@@ -13,8 +13,20 @@ import torch
 
 from . import _lib
 
+import os
+
 MODE_DOWN, MODE_UP, MODE_DENSE = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+TF32, TF32X3 = 0, 1
+_PRECISION_NAMES = {"tf32": TF32, "tf32x3": TF32X3}
+
+
+def default_precision() -> int:
+    """MDGAN_PRECISION = tf32x3 (default; ~fp32 accuracy, the parity mode) | tf32 (single-pass, cuDNN-TF32-like)."""
+    name = os.environ.get("MDGAN_PRECISION", "tf32x3").lower()
+    if name not in _PRECISION_NAMES:
+        raise ValueError(f"MDGAN_PRECISION must be one of {sorted(_PRECISION_NAMES)}, got {name!r}")
+    return _PRECISION_NAMES[name]
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -41,48 +53,72 @@ def n_pad_for(n: int) -> int:
 
 
 # ----------------------------------------------------------------------------- weights
-def pack_down(W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def packed_shape(mode: int, N: int, Cc: int, KK: int = 16, precision: int = TF32) -> Tuple[int, int]:
+    """Shape of the packed operand; tf32x3 stacks the `lo` matrix under the `hi` one (twice the rows)."""
+    m = 2 if precision == TF32X3 else 1
+    if mode == MODE_DOWN:
+        return m * n_pad_for(N), 16 * _pad(Cc, 32)
+    if mode == MODE_UP:
+        return m * 4 * n_pad_for(N), 4 * _pad(Cc, 32)
+    return m * KK * N, _pad(Cc, 32)
+
+
+def _split_of(out: torch.Tensor, rows_hi: int) -> int:
+    if out.shape[0] == rows_hi:
+        return 0
+    if out.shape[0] == 2 * rows_hi:
+        return 1
+    raise _lib.MdganLibraryError(f"packed weight buffer has {out.shape[0]} rows, expected {rows_hi} or {2 * rows_hi}")
+
+
+def pack_down(W: torch.Tensor, out: Optional[torch.Tensor] = None, precision: int = TF32) -> torch.Tensor:
     """W [N, C, 4, 4] -> [N_pad, 16*C_pad] (K-major, K = (tap, c)); conv fwd / convT dgrad operand."""
     N, Cc = W.shape[0], W.shape[1]
     Np, Cp = n_pad_for(N), _pad(Cc, 32)
     if out is None:
-        out = torch.empty((Np, 16 * Cp), device=W.device, dtype=torch.float32)
-    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 0, N, Cc, Np, Cp, 16, _stream()), "pack_down")
+        out = torch.empty(packed_shape(MODE_DOWN, N, Cc, precision=precision), device=W.device, dtype=torch.float32)
+    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 0, N, Cc, Np, Cp, 16, _split_of(out, Np), _stream()),
+               "pack_down")
     return out
 
 
-def pack_up(W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def pack_up(W: torch.Tensor, out: Optional[torch.Tensor] = None, precision: int = TF32) -> torch.Tensor:
     """W [C, N, 4, 4] -> [4 phases * N_pad, 4*C_pad]; convT fwd / conv dgrad operand."""
     Cc, N = W.shape[0], W.shape[1]
     Np, Cp = n_pad_for(N), _pad(Cc, 32)
     if out is None:
-        out = torch.empty((4 * Np, 4 * Cp), device=W.device, dtype=torch.float32)
-    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 1, N, Cc, Np, Cp, 16, _stream()), "pack_up")
+        out = torch.empty(packed_shape(MODE_UP, N, Cc, precision=precision), device=W.device, dtype=torch.float32)
+    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 1, N, Cc, Np, Cp, 16, _split_of(out, 4 * Np),
+                                              _stream()), "pack_up")
     return out
 
 
-def pack_dense(W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def pack_dense(W: torch.Tensor, out: Optional[torch.Tensor] = None, precision: int = TF32) -> torch.Tensor:
     """W [C, N, k, k] (ConvTranspose2d on a 1x1 input) -> [k*k*N, C_pad]."""
     Cc, N, KK = W.shape[0], W.shape[1], W.shape[2] * W.shape[3]
     Cp = _pad(Cc, 32)
     if out is None:
-        out = torch.empty((KK * N, Cp), device=W.device, dtype=torch.float32)
-    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 2, N, Cc, KK * N, Cp, KK, _stream()), "pack_dense")
+        out = torch.empty(packed_shape(MODE_DENSE, N, Cc, KK, precision), device=W.device, dtype=torch.float32)
+    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 2, N, Cc, KK * N, Cp, KK, _split_of(out, KK * N),
+                                              _stream()), "pack_dense")
     return out
 
 
 # ----------------------------------------------------------------------------- tensor-core GEMMs
 def conv_gemm(src: torch.Tensor, wpacked: torch.Tensor, mode: int, N: int, out: torch.Tensor,
               grid: Tuple[int, int, int], src_hw: Tuple[int, int], bias: Optional[torch.Tensor] = None,
-              out_nchw: bool = False, act_tanh: bool = False, round_tf32: bool = False, force_bn: int = 0) -> torch.Tensor:
-    """grid = (n_img, Hg, Wg): the low-resolution row grid; src is NHWC [n_img, Hs, Ws, C]."""
+              out_nchw: bool = False, act_tanh: bool = False, round_tf32: bool = False, accumulate: bool = False,
+              precision: int = TF32, force_bn: int = 0) -> torch.Tensor:
+    """grid = (n_img, Hg, Wg): the low-resolution row grid; src is NHWC [n_img, Hs, Ws, C].  With precision TF32X3
+    `wpacked` must hold the hi and lo matrices (pack_*(..., precision=TF32X3))."""
     n_img, Hg, Wg = grid
     Hs, Ws = src_hw
     Cc = src.shape[-1]
     phases = 4 if mode == MODE_UP else 1
-    N_pad = wpacked.shape[0] // phases
+    N_pad = wpacked.shape[0] // phases // (2 if precision == TF32X3 else 1)
     rc = _lib.load().mdgan_conv_gemm(_ptr(src), _ptr(wpacked), _ptr(out), _ptr(bias), n_img, Hg, Wg, Hs, Ws, Cc, mode,
-                                     N, N_pad, int(out_nchw), int(act_tanh), int(round_tf32), force_bn, _stream())
+                                     N, N_pad, int(out_nchw), int(act_tanh), int(round_tf32), int(accumulate), precision,
+                                     force_bn, _stream())
     _lib.check(rc, "conv_gemm")
     return out
 
@@ -92,10 +128,10 @@ def wgrad_splits(n_img: int, Hl: int, Wl: int, C1: int, C2: int, mode: int) -> i
 
 
 def wgrad_gemm(lo: torch.Tensor, hi: torch.Tensor, partial: torch.Tensor, grid: Tuple[int, int, int], mode: int,
-               splits: int) -> torch.Tensor:
+               splits: int, precision: int = TF32) -> torch.Tensor:
     n_img, Hl, Wl = grid
     rc = _lib.load().mdgan_wgrad_gemm(_ptr(lo), _ptr(hi), _ptr(partial), n_img, Hl, Wl, lo.shape[-1], hi.shape[-1],
-                                      mode, splits, _stream())
+                                      mode, splits, precision, _stream())
     _lib.check(rc, "wgrad_gemm")
     return partial
 

@@ -87,7 +87,7 @@ class _Recorder(TorchFunctionMode):
 
 
 _IGNORED = {"view", "squeeze", "flatten", "reshape", "contiguous", "size", "dim", "__get__", "to", "detach",
-            "is_cuda", "shape", "__getitem__", "unsqueeze"}
+            "is_cuda", "shape", "__getitem__", "unsqueeze", "add_"}
 
 
 def _param_names(module: nn.Module) -> Dict[int, str]:

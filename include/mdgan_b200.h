@@ -32,6 +32,12 @@ extern "C" {
 #define MDGAN_MODE_UP 1    /* 4 output phases: ConvTranspose2d forward, Conv2d data-grad   */
 #define MDGAN_MODE_DENSE 2 /* plain GEMM: ConvTranspose2d(k,s1,p0) on a 1x1 input          */
 
+/* precision of the tensor-core kernels.  TF32: one tcgen05.mma (kind::tf32) per K-slice on operands their
+ * producers rounded to TF32 -- as accurate as cuDNN's TF32 path.  TF32X3: error-compensated 3xTF32 (hi/lo operand
+ * split, three MMAs into the fp32 TMEM accumulator) -- ~fp32 accuracy; the parity mode. */
+#define MDGAN_PRECISION_TF32 0
+#define MDGAN_PRECISION_TF32X3 1
+
 #define MDGAN_ACT_NONE 0
 #define MDGAN_ACT_RELU 1
 #define MDGAN_ACT_LRELU 2
@@ -46,20 +52,23 @@ int mdgan_check_device(void);
  *   mode UP   : W [C][N][4][4]  -> out [4*N_pad][4*C_pad]          (ConvTranspose2d.weight, or Conv2d.weight for dgrad)
  *   mode DENSE: W [C][N][k][k]  -> out [KK*N][C_pad]               (first generator layer)
  * Replaces: the implicit weight access of nn.Conv2d / nn.ConvTranspose2d in CIFAR10.py:83-98,116-133,
- * CelebA.py:78-93,113-131. */
-int mdgan_pack_weights(const float* W, float* out, int mode, int N, int C, int N_pad, int C_pad, int KK, void* stream);
+ * CelebA.py:78-93,113-131.  split = 1 (precision tf32x3): `out` receives two matrices back to back,
+ * hi = tf32(w) and lo = tf32(w - hi). */
+int mdgan_pack_weights(const float* W, float* out, int mode, int N, int C, int N_pad, int C_pad, int KK, int split,
+                       void* stream);
 
 /* ---- implicit-GEMM convolution, tcgen05 (kind::tf32) + TMEM + TMA ---------------------------------------------
  * src  NHWC [n_img][Hs][Ws][C] (C % 32 == 0), wpacked from mdgan_pack_weights, rows = the low-resolution grid
  * (n_img, Hg, Wg).  Output: DOWN/DENSE -> [n_img][Hg][Wg][N]; UP -> [n_img][2Hg][2Wg][N]; NHWC, or NCHW when
- * out_nchw = 1 (image-side outputs).  bias (optional, [N]) is added, act = 1 applies tanh.  force_bn = 0 lets the
- * launcher pick the tile width.
+ * out_nchw = 1 (image-side outputs).  bias (optional, [N]) is added, act = 1 applies tanh.  accumulate = 1 (NCHW only)
+ * adds into dst: the feedbacks of all workers that share one generated batch are summed in place
+ * (actors/server.py:271-297).  force_bn = 0 lets the launcher pick the tile width.
  * Replaces: nn.Conv2d(k4,s2,p1) forward CIFAR10.py:88,92 / CelebA.py:81,85,88; nn.ConvTranspose2d forward
  * CIFAR10.py:118-130 / CelebA.py:113-131 (+ torch.tanh CIFAR10.py:131 / CelebA.py:140); and their data
  * gradients computed by loss.backward() (actors/worker.py:204,227) and torch.autograd.grad (actors/server.py:286). */
 int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img, int Hg, int Wg,
                     int Hs, int Ws, int C, int mode, int N, int N_pad, int out_nchw, int act, int round_tf32,
-                    int force_bn, void* stream);
+                    int accumulate, int precision, int force_bn, void* stream);
 
 /* ---- weight gradient, tcgen05 (kind::tf32, MN-major operands), split-K over pixels ----------------------------
  * partial[split][tap][C1][C2] = sum_p lo[p][c1] * hi[gather(p, tap)][c2]; mode DOWN = 16 taps of the k4 s2 p1
@@ -70,7 +79,7 @@ int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const fl
  * (actors/server.py:286-292). */
 int mdgan_wgrad_splits(int n_img, int Hl, int Wl, int C1, int C2, int mode);
 int mdgan_wgrad_gemm(const float* lo, const float* hi, float* partial, int n_img, int Hl, int Wl, int C1, int C2,
-                     int mode, int splits, void* stream);
+                     int mode, int splits, int precision, void* stream);
 int mdgan_wgrad_unpack(const float* partial, float* grad, int mode, int splits, int C1, int C1p, int C2, int N, int KK,
                        void* stream);
 int mdgan_reduce_slices(const float* partial, float* out, int slices, long long n, void* stream);

@@ -1,0 +1,39 @@
+"""Whole-loop parity on one GPU: N logical workers + server in one process (SURVEY.md build step 6) against the
+oracle, over several iterations including discriminator swaps.  Tolerances in tests/parity.py::TOL."""
+import pytest
+import torch
+
+from parity import run_engine_vs_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,n_workers,b,epochs,swap", [
+    ("CIFAR10", 1, 16, 3, 10**6),        # K = 1 baseline (no swap)
+    ("CIFAR10", 2, 8, 4, 2),             # swap at epoch 2
+    ("CIFAR10", 4, 8, 4, 1),             # BASELINE config 3 shape: N = 4, swap every epoch
+    ("MNIST_DCGAN", 2, 16, 3, 10**6),    # BASELINE config 2 shape
+    ("CelebA", 2, 4, 3, 1),
+    ("CelebA", 8, 2, 2, 1),              # BASELINE config 4 shape: N = 8 (k = 2)
+])
+def test_engine_matches_oracle(name, n_workers, b, epochs, swap):
+    r = run_engine_vs_oracle(name, n_workers, b, epochs, swap)
+    assert r["pairs_bit_exact"], "swap permutation must be bit-exact with the reference's RNG stream"
+    assert r["num_batches_tracked_exact"]
+    assert r["ok"], r
+
+
+def test_engine_local_epochs_two():
+    r = run_engine_vs_oracle("CIFAR10", 2, 8, 2, 10**6, local_epochs=2)
+    assert r["ok"], r
+
+
+def test_engine_refuses_cpu_and_mlp():
+    from mdgan_b200.engine import CudaNetFactory
+    from mdgan_b200.plan import UnsupportedModelError, extract_plan
+    from util import plugin
+
+    with pytest.raises(RuntimeError):
+        CudaNetFactory(torch.device("cpu"))
+    with pytest.raises(UnsupportedModelError):
+        extract_plan(plugin("MNIST").Discriminator(), "discriminator", (1, 28, 28))
