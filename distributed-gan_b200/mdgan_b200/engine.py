@@ -105,16 +105,28 @@ class MDGANEngine:
         self.iterations_done = 0
 
     # ------------------------------------------------------------------------------------------ phases
-    def draw_noise(self) -> None:
-        """server.py:219 -- consumes process 0's global torch RNG exactly like the reference in parity mode."""
+    def stage_inputs(self) -> None:
+        """Host half of an iteration: everything that touches host RNG / host memory and therefore cannot live in
+        the captured CUDA graph.  server.py:219 -- in parity mode (z_source == "host") the noise consumes process
+        0's global torch RNG exactly like the reference; real batches come from the host loaders in reference
+        order (worker.py:162-167).  Fills pinned staging buffers only; the device copies are in the device half."""
         kb = self.k * self.b
-        if self.cfg.z_source == "host":
+        if self.proc == 0 and self.cfg.z_source == "host":
             self.z_host.copy_(torch.randn((kb, self.cfg.z_dim, 1, 1)).view(kb, self.cfg.z_dim))
+        for n in self.local:
+            stage = getattr(self.real_sources[n], "stage", None)
+            if stage is not None:
+                stage()
+
+    def draw_noise(self) -> None:
+        if self.cfg.z_source == "host":
             self.z.copy_(self.z_host, non_blocking=True)
         else:
             self.z.normal_()
 
-    def generate(self) -> None:
+    def generate(self, staged: bool = False) -> None:
+        if not staged:
+            self.stage_inputs()
         if self.proc == 0:
             self.draw_noise()
             X = self.gen.forward(self.z)
@@ -153,10 +165,30 @@ class MDGANEngine:
         self.last_pairs = pairs
         return pairs
 
-    def iteration(self, epoch: int) -> None:
-        self.generate()
+    def device_iteration(self) -> None:
+        """Device half: H2D of the staged inputs, G forward, exchange, D steps + feedback, reduce, G backward, Adam."""
+        self.generate(staged=True)
         self.train_workers()
         self.update_generator()
+
+    def capture(self) -> None:
+        """Capture the device half of the steady-state iteration into one CUDA graph (at b <= 128 the
+        iteration is launch-bound).  Call after at least one eager iteration (lazy kernel attributes, tensor maps
+        and NCCL communicators must exist).  The swap stays outside the graph: it is host-driven and rare."""
+        if self.device.type != "cuda":
+            raise RuntimeError("CUDA graphs need a CUDA device")
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.device_iteration()
+        self.graph = graph
+
+    def iteration(self, epoch: int) -> None:
+        self.stage_inputs()
+        if getattr(self, "graph", None) is not None:
+            self.graph.replay()
+        else:
+            self.device_iteration()
         self.maybe_swap(epoch)
         self.iterations_done += 1
 

@@ -46,6 +46,7 @@ class FlatState:
             raise TypeError(f"only fp32 parameters and fp32/int64 buffers are supported (got {other})")
         self.fbuf_names = [n for n, _ in fbuf]
         self.ibuf_names = [n for n, _ in ibuf]
+        self.key_order = list(module.state_dict().keys())
         self.n_params = sum(p.numel() for p in module.parameters())
         n_f = self.n_params + sum(b.numel() for _, b in fbuf)
         self.state_f32 = torch.zeros(n_f, device=device, dtype=torch.float32)
@@ -87,13 +88,26 @@ class FlatState:
         for n, bf in module.named_buffers():
             bf.data.copy_(self.b[n].to(bf.device))
 
+    @torch.no_grad()
+    def load_adam(self, optimizer: torch.optim.Optimizer, module: nn.Module) -> None:
+        """Adopt the moments and step count of a torch.optim.Adam that optimises `module.parameters()` (resume /
+        hand-over of a run started elsewhere; the reference never saves optimizer state)."""
+        self.m.zero_()
+        self.v.zero_()
+        step, off = 0, 0
+        for prm in module.parameters():
+            k = prm.numel()
+            st = optimizer.state.get(prm, {})
+            if st:
+                self.m[off: off + k].copy_(st["exp_avg"].detach().reshape(-1).to(self.device, torch.float32))
+                self.v[off: off + k].copy_(st["exp_avg_sq"].detach().reshape(-1).to(self.device, torch.float32))
+                step = int(st["step"])
+            off += k
+        self.step.fill_(step)
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
-        out = {}
-        for n in self.param_names:
-            out[n] = self.p[n].detach().cpu().clone()
-        for n in self.fbuf_names + self.ibuf_names:
-            out[n] = self.b[n].detach().cpu().clone()
-        return out
+        """Host copy in the module's own `state_dict()` key order (what torch.save of the reference writes)."""
+        return {n: (self.p[n] if n in self.p else self.b[n]).detach().cpu().clone() for n in self.key_order}
 
 
 def _cpu_copy(module: nn.Module) -> nn.Module:

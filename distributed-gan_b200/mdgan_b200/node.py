@@ -49,9 +49,32 @@ class _DeviceBatches:
         self.pinned = torch.empty((stream.batch_size, *shape), dtype=torch.float32, pin_memory=True)
         self.dev = torch.empty((stream.batch_size, *shape), dtype=torch.float32, device=device)
 
-    def __call__(self) -> torch.Tensor:
+    def stage(self) -> None:
+        """Host half: next batch of the reference-order loader into the pinned buffer."""
         self.pinned.copy_(self.stream.next())
+
+    def __call__(self) -> torch.Tensor:
+        """Device half (graph-capturable): H2D from the pinned buffer."""
         self.dev.copy_(self.pinned, non_blocking=True)
+        return self.dev
+
+
+class DeviceResidentBatches:
+    """Real batches already resident in HBM: the worker's whole shard is uploaded once, in the reference's batch
+    order for the first epoch, and every iteration a device-to-device copy moves the next batch into the fixed
+    buffer the (possibly graph-captured) step reads.  Used when the shard fits on the device (synthetic-data
+    benchmarks, small datasets); `_DeviceBatches` streams from the host otherwise."""
+
+    def __init__(self, stream: routing.RealBatchStream, device: torch.device, shape, n_batches: int):
+        self.ring = torch.stack([stream.next() for _ in range(n_batches)]).to(device)
+        self.dev = torch.empty((stream.batch_size, *shape), dtype=torch.float32, device=device)
+        self.i = 0
+
+    def stage(self) -> None:
+        self.dev.copy_(self.ring[self.i])
+        self.i = (self.i + 1) % self.ring.shape[0]
+
+    def __call__(self) -> torch.Tensor:
         return self.dev
 
 

@@ -29,6 +29,24 @@ def default_precision() -> int:
     return _PRECISION_NAMES[name]
 
 
+# Optional launch observer (bench.py / tools): called as observer(name, n_kernels, flops, bytes) and must return a
+# context manager entered around the launch.  flops / bytes are the ALGORITHMIC work of the call.
+_observer = None
+
+
+def set_observer(observer) -> None:
+    global _observer
+    _observer = observer
+
+
+def _run(name: str, n_kernels: int, flops: float, nbytes: float, call) -> None:
+    if _observer is None:
+        _lib.check(call(), name)
+        return
+    with _observer(name, n_kernels, flops, nbytes):
+        _lib.check(call(), name)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     if t is None:
         return None
@@ -77,8 +95,8 @@ def pack_down(W: torch.Tensor, out: Optional[torch.Tensor] = None, precision: in
     Np, Cp = n_pad_for(N), _pad(Cc, 32)
     if out is None:
         out = torch.empty(packed_shape(MODE_DOWN, N, Cc, precision=precision), device=W.device, dtype=torch.float32)
-    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 0, N, Cc, Np, Cp, 16, _split_of(out, Np), _stream()),
-               "pack_down")
+    _run("pack_weights", 1, 0, 4 * (W.numel() + out.numel()),
+         lambda: _lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 0, N, Cc, Np, Cp, 16, _split_of(out, Np), _stream()))
     return out
 
 
@@ -88,8 +106,9 @@ def pack_up(W: torch.Tensor, out: Optional[torch.Tensor] = None, precision: int 
     Np, Cp = n_pad_for(N), _pad(Cc, 32)
     if out is None:
         out = torch.empty(packed_shape(MODE_UP, N, Cc, precision=precision), device=W.device, dtype=torch.float32)
-    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 1, N, Cc, Np, Cp, 16, _split_of(out, 4 * Np),
-                                              _stream()), "pack_up")
+    _run("pack_weights", 1, 0, 4 * (W.numel() + out.numel()),
+         lambda: _lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 1, N, Cc, Np, Cp, 16, _split_of(out, 4 * Np),
+                                                _stream()))
     return out
 
 
@@ -99,8 +118,9 @@ def pack_dense(W: torch.Tensor, out: Optional[torch.Tensor] = None, precision: i
     Cp = _pad(Cc, 32)
     if out is None:
         out = torch.empty(packed_shape(MODE_DENSE, N, Cc, KK, precision), device=W.device, dtype=torch.float32)
-    _lib.check(_lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 2, N, Cc, KK * N, Cp, KK, _split_of(out, KK * N),
-                                              _stream()), "pack_dense")
+    _run("pack_weights", 1, 0, 4 * (W.numel() + out.numel()),
+         lambda: _lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 2, N, Cc, KK * N, Cp, KK, _split_of(out, KK * N),
+                                                _stream()))
     return out
 
 
@@ -116,10 +136,13 @@ def conv_gemm(src: torch.Tensor, wpacked: torch.Tensor, mode: int, N: int, out: 
     Cc = src.shape[-1]
     phases = 4 if mode == MODE_UP else 1
     N_pad = wpacked.shape[0] // phases // (2 if precision == TF32X3 else 1)
-    rc = _lib.load().mdgan_conv_gemm(_ptr(src), _ptr(wpacked), _ptr(out), _ptr(bias), n_img, Hg, Wg, Hs, Ws, Cc, mode,
-                                     N, N_pad, int(out_nchw), int(act_tanh), int(round_tf32), int(accumulate), precision,
-                                     force_bn, _stream())
-    _lib.check(rc, "conv_gemm")
+    taps = {MODE_DOWN: 16, MODE_UP: 16, MODE_DENSE: 1}[mode]  # UP: 4 phases x 4 taps per low-res position
+    flops = 2.0 * n_img * Hg * Wg * taps * Cc * N
+    nbytes = 4.0 * (src.numel() + out.numel() + wpacked.numel())
+    _run(("conv_down", "conv_up", "conv_dense")[mode], 1, flops, nbytes,
+         lambda: _lib.load().mdgan_conv_gemm(_ptr(src), _ptr(wpacked), _ptr(out), _ptr(bias), n_img, Hg, Wg, Hs, Ws, Cc,
+                                             mode, N, N_pad, int(out_nchw), int(act_tanh), int(round_tf32),
+                                             int(accumulate), precision, force_bn, _stream()))
     return out
 
 
@@ -130,21 +153,25 @@ def wgrad_splits(n_img: int, Hl: int, Wl: int, C1: int, C2: int, mode: int) -> i
 def wgrad_gemm(lo: torch.Tensor, hi: torch.Tensor, partial: torch.Tensor, grid: Tuple[int, int, int], mode: int,
                splits: int, precision: int = TF32) -> torch.Tensor:
     n_img, Hl, Wl = grid
-    rc = _lib.load().mdgan_wgrad_gemm(_ptr(lo), _ptr(hi), _ptr(partial), n_img, Hl, Wl, lo.shape[-1], hi.shape[-1],
-                                      mode, splits, precision, _stream())
-    _lib.check(rc, "wgrad_gemm")
+    taps = 16 if mode == MODE_DOWN else 1
+    flops = 2.0 * n_img * Hl * Wl * taps * lo.shape[-1] * hi.shape[-1]
+    nbytes = 4.0 * (lo.numel() + hi.numel() + taps * lo.shape[-1] * hi.shape[-1])
+    _run("wgrad_gemm", 1, flops, nbytes,
+         lambda: _lib.load().mdgan_wgrad_gemm(_ptr(lo), _ptr(hi), _ptr(partial), n_img, Hl, Wl, lo.shape[-1],
+                                              hi.shape[-1], mode, splits, precision, _stream()))
     return partial
 
 
 def wgrad_unpack(partial: torch.Tensor, grad: torch.Tensor, mode: int, splits: int, C1: int, C1p: int, C2: int,
                  N: int = 0, KK: int = 0) -> torch.Tensor:
-    rc = _lib.load().mdgan_wgrad_unpack(_ptr(partial), _ptr(grad), mode, splits, C1, C1p, C2, N, KK, _stream())
-    _lib.check(rc, "wgrad_unpack")
+    _run("wgrad_unpack", 1, 0, 4.0 * grad.numel() * (splits + 1),
+         lambda: _lib.load().mdgan_wgrad_unpack(_ptr(partial), _ptr(grad), mode, splits, C1, C1p, C2, N, KK, _stream()))
     return grad
 
 
 def reduce_slices(partial: torch.Tensor, out: torch.Tensor, slices: int) -> torch.Tensor:
-    _lib.check(_lib.load().mdgan_reduce_slices(_ptr(partial), _ptr(out), slices, out.numel(), _stream()), "reduce_slices")
+    _run("reduce_slices", 1, 0, 4.0 * out.numel() * (slices + 1),
+         lambda: _lib.load().mdgan_reduce_slices(_ptr(partial), _ptr(out), slices, out.numel(), _stream()))
     return out
 
 
@@ -152,9 +179,9 @@ def reduce_slices(partial: torch.Tensor, out: torch.Tensor, slices: int) -> torc
 def thin_down(img: torch.Tensor, W: torch.Tensor, out: torch.Tensor, act: int = ACT_NONE, slope: float = 0.0,
               round_tf32: bool = False) -> torch.Tensor:
     n, ci, Hi, Wi = img.shape
-    rc = _lib.load().mdgan_thin_down(_ptr(img), _ptr(W), _ptr(out), n, ci, Hi, Wi, W.shape[0], act, slope,
-                                     int(round_tf32), _stream())
-    _lib.check(rc, "thin_down")
+    _run("thin_down", 1, 2.0 * out.numel() * 16 * ci, 4.0 * (img.numel() + out.numel() + W.numel()),
+         lambda: _lib.load().mdgan_thin_down(_ptr(img), _ptr(W), _ptr(out), n, ci, Hi, Wi, W.shape[0], act, slope,
+                                             int(round_tf32), _stream()))
     return out
 
 
@@ -165,8 +192,8 @@ def thin_wgrad_slices(n_img: int, Hl: int, Wl: int) -> int:
 def thin_wgrad(feat: torch.Tensor, img: torch.Tensor, partial: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
     n, ci, Hi, Wi = img.shape
     Hl, Wl, C1 = Hi // 2, Wi // 2, feat.shape[-1]
-    lib = _lib.load()
-    _lib.check(lib.mdgan_thin_wgrad(_ptr(feat), _ptr(img), _ptr(partial), n, ci, Hl, Wl, C1, _stream()), "thin_wgrad")
+    _run("thin_wgrad", 1, 2.0 * feat.numel() * 16 * ci, 4.0 * (feat.numel() + img.numel() + grad.numel()),
+         lambda: _lib.load().mdgan_thin_wgrad(_ptr(feat), _ptr(img), _ptr(partial), n, ci, Hl, Wl, C1, _stream()))
     return reduce_slices(partial, grad, thin_wgrad_slices(n, Hl, Wl))
 
 
@@ -177,56 +204,61 @@ def bn_workspace_floats(G: int, Pg: int, Cc: int) -> int:
 
 def bn_forward(x, out, gamma, beta, running_mean, running_var, nbt, stats, workspace, G, Pg, Cc, act, slope,
                round_tf32=False, eps=1e-5, momentum=0.1):
-    rc = _lib.load().mdgan_bn_forward(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
-                                      _ptr(nbt), _ptr(stats), _ptr(workspace), G, Pg, Cc, eps, momentum, act, slope,
-                                      int(round_tf32), _stream())
-    _lib.check(rc, "bn_forward")
+    _run("bn_forward", 3, 0, 4.0 * 2 * G * Pg * Cc,
+         lambda: _lib.load().mdgan_bn_forward(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                                              _ptr(running_var), _ptr(nbt), _ptr(stats), _ptr(workspace), G, Pg, Cc,
+                                              eps, momentum, act, slope, int(round_tf32), _stream()))
     return out
 
 
 def bn_backward(da, x, stats, dx, dgamma, dbeta, sums, workspace, G, Pg, Cc, act, slope, round_tf32=False):
-    rc = _lib.load().mdgan_bn_backward(_ptr(da), _ptr(x), _ptr(stats), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(sums),
-                                       _ptr(workspace), G, Pg, Cc, act, slope, int(round_tf32), _stream())
-    _lib.check(rc, "bn_backward")
+    _run("bn_backward", 3, 0, 4.0 * 3 * G * Pg * Cc,
+         lambda: _lib.load().mdgan_bn_backward(_ptr(da), _ptr(x), _ptr(stats), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                                               _ptr(sums), _ptr(workspace), G, Pg, Cc, act, slope, int(round_tf32),
+                                               _stream()))
     return dx
 
 
 def act_backward(da, a, dz, act, slope, round_tf32=False):
-    _lib.check(_lib.load().mdgan_act_backward(_ptr(da), _ptr(a), _ptr(dz), a.numel(), act, slope, int(round_tf32),
-                                              _stream()), "act_backward")
+    _run("act_backward", 1, 0, 4.0 * 3 * a.numel(),
+         lambda: _lib.load().mdgan_act_backward(_ptr(da), _ptr(a), _ptr(dz), a.numel(), act, slope, int(round_tf32),
+                                                _stream()))
     return dz
 
 
 def tanh_backward(s, x, out, scale: float):
-    _lib.check(_lib.load().mdgan_tanh_backward(_ptr(s), _ptr(x), _ptr(out), x.numel(), scale, _stream()), "tanh_backward")
+    _run("tanh_backward", 1, 0, 4.0 * 3 * x.numel(),
+         lambda: _lib.load().mdgan_tanh_backward(_ptr(s), _ptr(x), _ptr(out), x.numel(), scale, _stream()))
     return out
 
 
 # ----------------------------------------------------------------------------- head / loss / optimiser
 def head_forward(a, w, label, prob, loss_terms, dlogit, loss, G, b, HW, Cc):
-    rc = _lib.load().mdgan_head_forward(_ptr(a), _ptr(w), _ptr(label), _ptr(prob), _ptr(loss_terms), _ptr(dlogit),
-                                        _ptr(loss), G, b, HW, Cc, _stream())
-    _lib.check(rc, "head_forward")
+    _run("head_forward", 2, 2.0 * G * b * HW * Cc, 4.0 * (G * b * HW * Cc + HW * Cc),
+         lambda: _lib.load().mdgan_head_forward(_ptr(a), _ptr(w), _ptr(label), _ptr(prob), _ptr(loss_terms),
+                                                _ptr(dlogit), _ptr(loss), G, b, HW, Cc, _stream()))
 
 
 def head_backward(a, w, dlogit, da, dw, n_total, HW, Cc):
-    rc = _lib.load().mdgan_head_backward(_ptr(a), _ptr(w), _ptr(dlogit), _ptr(da), _ptr(dw), n_total, HW, Cc, _stream())
-    _lib.check(rc, "head_backward")
+    _run("head_backward", 1, 4.0 * n_total * HW * Cc, 4.0 * (2 * n_total * HW * Cc + 2 * HW * Cc),
+         lambda: _lib.load().mdgan_head_backward(_ptr(a), _ptr(w), _ptr(dlogit), _ptr(da), _ptr(dw), n_total, HW, Cc,
+                                                 _stream()))
 
 
 def adam_step(p, g, m, v, step_count, lr, beta1, beta2, eps=1e-8):
-    rc = _lib.load().mdgan_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(step_count), lr, beta1, beta2,
-                                     eps, _stream())
-    _lib.check(rc, "adam_step")
+    _run("adam_step", 2, 0, 28.0 * p.numel(),
+         lambda: _lib.load().mdgan_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(step_count), lr, beta1,
+                                             beta2, eps, _stream()))
 
 
 def pad_rows(x, out, round_tf32=False):
     rows, cin = x.shape
-    _lib.check(_lib.load().mdgan_pad_rows(_ptr(x), _ptr(out), rows, cin, out.shape[1], int(round_tf32), _stream()),
-               "pad_rows")
+    _run("pad_rows", 1, 0, 4.0 * (x.numel() + out.numel()),
+         lambda: _lib.load().mdgan_pad_rows(_ptr(x), _ptr(out), rows, cin, out.shape[1], int(round_tf32), _stream()))
     return out
 
 
 def sum_slices(x, out, count: int, stride: int):
-    _lib.check(_lib.load().mdgan_sum_slices(_ptr(x), _ptr(out), out.numel(), count, stride, _stream()), "sum_slices")
+    _run("sum_slices", 1, 0, 4.0 * out.numel() * (count + 1),
+         lambda: _lib.load().mdgan_sum_slices(_ptr(x), _ptr(out), out.numel(), count, stride, _stream()))
     return out

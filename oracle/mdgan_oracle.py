@@ -106,7 +106,7 @@ def d_train_step(D: nn.Module, opt: torch.optim.Optimizer, real: torch.Tensor, x
     """worker.py:197-206 -- one local epoch of discriminator training; returns d_loss."""
     b = real.shape[0]
     crit = nn.BCELoss()
-    ones, zeros = torch.ones(b), torch.zeros(b)
+    ones, zeros = torch.ones(b, dtype=real.dtype), torch.zeros(b, dtype=real.dtype)
     D.zero_grad()
     d_loss_real = crit(D(real), ones)
     d_loss_fake = crit(D(x_d), zeros)
@@ -119,7 +119,7 @@ def d_train_step(D: nn.Module, opt: torch.optim.Optimizer, real: torch.Tensor, x
 def d_feedback(D: nn.Module, x_g: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """worker.py:220-233 -- F_n = d BCE(D(X_g), 1) / d X_g (D in train mode); returns (loss_gen, F_n)."""
     x = x_g.detach().clone().requires_grad_(True)
-    loss_gen = nn.BCELoss()(D(x), torch.ones(x.shape[0]))
+    loss_gen = nn.BCELoss()(D(x), torch.ones(x.shape[0], dtype=x.dtype))
     loss_gen.backward()
     return loss_gen.detach(), x.grad.detach()
 
@@ -161,7 +161,12 @@ class OracleMDGAN:
         swap_interval: int = 10**9,
         local_epochs: int = 1,
         iid: bool = True,
+        dtype: torch.dtype = torch.float32,
     ):
+        # dtype=float64 builds the "exact arithmetic" twin used by the tests to calibrate how far two correct
+        # implementations of this (chaotic: ReLU gates + Adam's sign-like first steps) loop drift apart from
+        # rounding alone; models are initialised in fp32 from the same RNG stream, then widened.
+        self.dtype = dtype
         self.N, self.b, self.z_dim, self.shape = n_workers, batch_size, z_dim, tuple(image_shape)
         self.k = num_generated_batches(n_workers)
         self.swap_interval, self.local_epochs = swap_interval, local_epochs
@@ -171,6 +176,7 @@ class OracleMDGAN:
             self.G = generator_cls().to(dtype=torch.float32)
             self.G.apply(weights_init)
             self.G.train()  # server.py:171
+        self.G.to(dtype)
         self.opt_g = torch.optim.Adam(self.G.parameters(), lr=generator_lr, betas=(beta_1, beta_2))
         self.D: List[nn.Module] = []
         self.opt_d: List[torch.optim.Optimizer] = []
@@ -179,7 +185,7 @@ class OracleMDGAN:
                 d = discriminator_cls().to(dtype=torch.float32)
                 d.apply(weights_init)
                 d.train()  # worker.py:193
-            self.D.append(d)
+            self.D.append(d.to(dtype))
             self.opt_d.append(torch.optim.Adam(d.parameters(), lr=discriminator_lr, betas=(beta_1, beta_2)))
         self.shards = split_dataset(len(dataset), n_workers, iid)
         self.real = [_RealBatches(dataset, self.shards[n], batch_size) for n in range(n_workers)]
@@ -199,20 +205,25 @@ class OracleMDGAN:
             torch.set_rng_state(outer)
 
     # ---- one generator iteration (a reference "epoch")
-    def step(self, epoch: int, record: bool = True) -> Dict[str, object]:
+    def step(self, epoch: int, record: bool = True, z: Optional[torch.Tensor] = None,
+             replay_reals: Optional[Sequence[torch.Tensor]] = None, pairs: Optional[torch.Tensor] = None) -> Dict[str, object]:
+        """z / replay_reals / pairs: replay another run's random draws instead of consuming this oracle's RNG streams and
+        data loaders (used by the tests to run the fp64 twin on exactly the reference's inputs)."""
         N, k, b = self.N, self.k, self.b
         out: Dict[str, object] = {}
-        with self._as_rank(0):
-            z = torch.randn((k * b, self.z_dim, 1, 1))  # server.py:219
+        if z is None:
+            with self._as_rank(0):
+                z = torch.randn((k * b, self.z_dim, 1, 1))  # server.py:219
+        z = z.to(self.dtype)
         X = self.G(z)  # server.py:220 (train-mode BN over all k*b samples)
         K = torch.chunk(X, k)  # server.py:223
-        feedbacks = torch.zeros((N, b, *self.shape))
+        feedbacks = torch.zeros((N, b, *self.shape), dtype=self.dtype)
         d_losses, g_losses, reals = [], [], []
         for n in range(N):
             ig, id_ = route(n, k)
             x_g, x_d = K[ig].detach(), K[id_].detach()
             with self._as_rank(n + 1):
-                real = self.real[n].next()  # worker.py:162-167
+                real = (self.real[n].next() if replay_reals is None else replay_reals[n]).to(self.dtype)  # worker.py:162-167
                 losses = torch.zeros(self.local_epochs)
                 for l in range(self.local_epochs):  # worker.py:193-213
                     losses[l] = d_train_step(self.D[n], self.opt_d[n], real, x_d)
@@ -227,10 +238,13 @@ class OracleMDGAN:
         for p, g in zip(self.G.parameters(), delta_w):  # server.py:308-312
             p.grad = g.detach()
         self.opt_g.step()
-        pairs = None
+        replay_pairs, pairs = pairs, None
         if swap_due(epoch, self.swap_interval, N):  # server.py:315-333, worker.py:239-284
-            with self._as_rank(0):
-                pairs = draw_swap_pairs(N)
+            if replay_pairs is not None:
+                pairs = replay_pairs
+            else:
+                with self._as_rank(0):
+                    pairs = draw_swap_pairs(N)
             for a, c in pairs.tolist():
                 sa = {kk: v.detach().clone() for kk, v in self.D[a - 1].state_dict().items()}
                 sc = {kk: v.detach().clone() for kk, v in self.D[c - 1].state_dict().items()}

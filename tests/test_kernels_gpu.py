@@ -34,6 +34,8 @@ def dev():
                                         (4, 128, 256, 8, 0), (3, 256, 512, 8, 0), (64, 64, 128, 32, 0)])
 @pytest.mark.parametrize("prec,tol", PRECISIONS)
 def test_conv_down(ops, dev, n, C, N, H, bn, prec, tol):
+    if prec == 1 and bn > 64:
+        pytest.skip("tf32x3 tiles are at most 64 wide (TMEM holds the split accumulators)")
     torch.manual_seed(1)
     x, W = torch.randn(n, C, H, H), torch.randn(N, C, 4, 4) * 0.05
     bias = torch.randn(N) * 0.1
