@@ -32,6 +32,7 @@ SIGNATURES = {
     "mdgan_bn_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "mdgan_act_backward": (_i, [_p, _p, _p, _ll, _i, _f, _i, _p]),
     "mdgan_tanh_backward": (_i, [_p, _p, _p, _ll, _f, _p]),
+    "mdgan_head_pack": (_i, [_p, _p, _i, _i, _p]),
     "mdgan_head_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "mdgan_head_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "mdgan_adam_step": (_i, [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _p]),

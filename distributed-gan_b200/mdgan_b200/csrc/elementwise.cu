@@ -120,38 +120,56 @@ __global__ void bn_partial_kernel(const float* __restrict__ x, float* __restrict
 
 // Stage 2: per group (in order) mean / biased var -> scale, shift; running stats with momentum 0.1 and unbiased
 // variance, num_batches_tracked += G.  stats layout: [G][4][C] = mean, invstd, scale, shift.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, long long* __restrict__ nbt,
-                                   float* __restrict__ stats, int G, int Pg, int C, int chunks_per_group, float eps,
-                                   float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt != nullptr) *nbt += G;
-  if (c >= C) return;
-  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+// Block = 32 channels x 8 chunk-lanes: the chunk partials of a channel are summed by 8 threads in fp64 and combined
+// through shared memory (a single thread walking all ~300 chunks cost 40-60 us of pure latency per launch).
+constexpr int kFinLanes = 8;
+__global__ void __launch_bounds__(32 * kFinLanes)
+bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
+                   float* __restrict__ stats, int G, int Pg, int C, int chunks_per_group, float eps, float momentum) {
+  __shared__ double red[2][kFinLanes][32];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += G;
+  const bool ok = c < C;
+  float rm = 0.f, rv = 0.f;
+  if (ok && lane == 0) { rm = running_mean ? running_mean[c] : 0.f; rv = running_var ? running_var[c] : 0.f; }
   for (int g = 0; g < G; ++g) {
     double s = 0.0, ss = 0.0;
-    for (int ch = 0; ch < chunks_per_group; ++ch) {
-      const float* pp = partial + ((long long)(g * chunks_per_group + ch)) * 2 * C;
-      s += pp[c];
-      ss += pp[C + c];
+    if (ok) {
+      for (int ch = lane; ch < chunks_per_group; ch += kFinLanes) {
+        const float* pp = partial + ((long long)(g * chunks_per_group + ch)) * 2 * C;
+        s += pp[c];
+        ss += pp[C + c];
+      }
     }
-    const double mean = s / Pg;
-    double var = ss / Pg - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = gamma[c] * invstd;
-    float* st = stats + (long long)g * 4 * C;
-    st[c] = (float)mean;
-    st[C + c] = invstd;
-    st[2 * C + c] = sc;
-    st[3 * C + c] = beta[c] - (float)mean * sc;
-    const float unbiased = (float)(var * ((double)Pg / (double)(Pg > 1 ? Pg - 1 : 1)));
-    rm = (1.f - momentum) * rm + momentum * (float)mean;
-    rv = (1.f - momentum) * rv + momentum * unbiased;
+    red[0][lane][cl] = s;
+    red[1][lane][cl] = ss;
+    __syncthreads();
+    if (ok && lane == 0) {
+      s = 0.0; ss = 0.0;
+#pragma unroll
+      for (int l = 0; l < kFinLanes; ++l) { s += red[0][l][cl]; ss += red[1][l][cl]; }
+      const double mean = s / Pg;
+      double var = ss / Pg - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float sc = gamma[c] * invstd;
+      float* st = stats + (long long)g * 4 * C;
+      st[c] = (float)mean;
+      st[C + c] = invstd;
+      st[2 * C + c] = sc;
+      st[3 * C + c] = beta[c] - (float)mean * sc;
+      const float unbiased = (float)(var * ((double)Pg / (double)(Pg > 1 ? Pg - 1 : 1)));
+      rm = (1.f - momentum) * rm + momentum * (float)mean;
+      rv = (1.f - momentum) * rv + momentum * unbiased;
+    }
+    __syncthreads();
   }
-  if (running_mean) running_mean[c] = rm;
-  if (running_var) running_var[c] = rv;
+  if (ok && lane == 0) {
+    if (running_mean) running_mean[c] = rm;
+    if (running_var) running_var[c] = rv;
+  }
 }
 
 // act: 0 none, 1 ReLU, 2 LeakyReLU(slope)
@@ -233,26 +251,42 @@ __global__ void bn_bwd_partial_kernel(const float* __restrict__ da, const float*
 }
 
 // Backward stage 2: sums[g][2][C] (sum dy, sum dy*xhat); dgamma/dbeta = totals over all groups (optional).
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int C,
-                                       int chunks_per_group) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// Same 32-channel x 8-lane layout as bn_finalize_kernel.
+__global__ void __launch_bounds__(32 * kFinLanes)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, int G, int C, int chunks_per_group) {
+  __shared__ double red[2][kFinLanes][32];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const bool ok = c < C;
   double tg = 0.0, tb = 0.0;
   for (int g = 0; g < G; ++g) {
     double s = 0.0, ss = 0.0;
-    for (int ch = 0; ch < chunks_per_group; ++ch) {
-      const float* pp = partial + ((long long)(g * chunks_per_group + ch)) * 2 * C;
-      s += pp[c];
-      ss += pp[C + c];
+    if (ok) {
+      for (int ch = lane; ch < chunks_per_group; ch += kFinLanes) {
+        const float* pp = partial + ((long long)(g * chunks_per_group + ch)) * 2 * C;
+        s += pp[c];
+        ss += pp[C + c];
+      }
     }
-    sums[(long long)g * 2 * C + c] = (float)s;
-    sums[(long long)g * 2 * C + C + c] = (float)ss;
-    tb += s;
-    tg += ss;
+    red[0][lane][cl] = s;
+    red[1][lane][cl] = ss;
+    __syncthreads();
+    if (ok && lane == 0) {
+      s = 0.0; ss = 0.0;
+#pragma unroll
+      for (int l = 0; l < kFinLanes; ++l) { s += red[0][l][cl]; ss += red[1][l][cl]; }
+      sums[(long long)g * 2 * C + c] = (float)s;
+      sums[(long long)g * 2 * C + C + c] = (float)ss;
+      tb += s;
+      tg += ss;
+    }
+    __syncthreads();
   }
-  if (dgamma) dgamma[c] = (float)tg;
-  if (dbeta) dbeta[c] = (float)tb;
+  if (ok && lane == 0) {
+    if (dgamma) dgamma[c] = (float)tg;
+    if (dbeta) dbeta[c] = (float)tb;
+  }
 }
 
 // Backward stage 3: dx = scale * (dy - mean(dy) - xhat * mean(dy*xhat))
@@ -311,38 +345,52 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ s, const float* __rest
 }
 
 // ----------------------------------------------------------------------------------------------- discriminator head
-// logits[n] = <a[n, :], w>,  a is NHWC [n, HW, C], w is PyTorch [1, C, H, W] (index c*HW + hw).
+// wt[hw*C + c] = w[c*HW + hw]: the head weight re-ordered once per optimiser step to the NHWC order of the activations
+// so that the per-sample dot products below read both operands with coalesced float4 loads.
+__global__ void head_pack_kernel(const float* __restrict__ w, float* __restrict__ wt, int HW, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW * C) return;
+  const int hw = i / C, c = i - hw * C;
+  wt[i] = w[c * HW + hw];
+}
+
+// logits[n] = <a[n, :], wt>,  a is NHWC [n, HW, C], wt from head_pack_kernel.
 // p = sigmoid(logit); per-sample BCE term with the log clamp at -100; dlogit = dBCE/dlogit * (1/b).
-// Labels: samples of group g (n / b) use label[g].  One warp per sample.
-__global__ void head_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ label,
-                                float* __restrict__ prob, float* __restrict__ loss_terms, float* __restrict__ dlogit,
-                                int n_total, int b, int HW, int C) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= n_total) return;
-  const int L = HW * C;
-  const float* row = a + (long long)warp * L;
+// Labels: samples of group g (n / b) use label[g].  One 256-thread block per sample.
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float* __restrict__ a, const float* __restrict__ wt, const float* __restrict__ label,
+                float* __restrict__ prob, float* __restrict__ loss_terms, float* __restrict__ dlogit, int n_total, int b,
+                int L) {
+  __shared__ float red[8];
+  const int n = blockIdx.x;
+  const float4* row = reinterpret_cast<const float4*>(a + (long long)n * L);
+  const float4* w4 = reinterpret_cast<const float4*>(wt);
   float acc = 0.f;
-  for (int l = lane * 4; l < L; l += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(row + l);
-    const int hw = l / C, c = l - hw * C;
-    acc = fmaf(v.x, __ldg(w + (c + 0) * HW + hw), acc);
-    acc = fmaf(v.y, __ldg(w + (c + 1) * HW + hw), acc);
-    acc = fmaf(v.z, __ldg(w + (c + 2) * HW + hw), acc);
-    acc = fmaf(v.w, __ldg(w + (c + 3) * HW + hw), acc);
+  for (int i = threadIdx.x; i < (L >> 2); i += 256) {
+    const float4 v = row[i];
+    const float4 u = __ldg(w4 + i);
+    acc = fmaf(v.x, u.x, acc);
+    acc = fmaf(v.y, u.y, acc);
+    acc = fmaf(v.z, u.z, acc);
+    acc = fmaf(v.w, u.w, acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) {
-    const float y = label[warp / b];
-    const float p = 1.f / (1.f + expf(-acc));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float logit = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) logit += red[i];
+    const float y = label[n / b];
+    const float p = 1.f / (1.f + expf(-logit));
     const float lp = fmaxf(logf(p), -100.f);
     const float l1p = fmaxf(log1pf(-p), -100.f);
-    prob[warp] = p;
-    loss_terms[warp] = (y - 1.f) * l1p - y * lp;
+    prob[n] = p;
+    loss_terms[n] = (y - 1.f) * l1p - y * lp;
     const float pq = (1.f - p) * p;
     // BCELoss backward: (p - y) / max(p(1-p), 1e-12) / b; sigmoid backward: * p(1-p)
-    dlogit[warp] = ((p - y) / fmaxf(pq, 1e-12f)) * (1.f / (float)b) * pq;
+    dlogit[n] = ((p - y) / fmaxf(pq, 1e-12f)) * (1.f / (float)b) * pq;
   }
 }
 
@@ -369,15 +417,15 @@ __global__ void head_loss_kernel(const float* __restrict__ loss_terms, float* __
   if (threadIdx.x == 0) loss[G] = total;
 }
 
-// da[n, l] = dlogit[n] * w[l];  dw[c*HW + hw] = sum_n dlogit[n] * a[n, l]  (dw optional)
-__global__ void head_bwd_kernel(const float* __restrict__ a, const float* __restrict__ w,
+// da[n, l] = dlogit[n] * wt[l];  dw[c*HW + hw] = sum_n dlogit[n] * a[n, l]  (dw optional, PyTorch layout)
+__global__ void head_bwd_kernel(const float* __restrict__ a, const float* __restrict__ wt,
                                 const float* __restrict__ dlogit, float* __restrict__ da, float* __restrict__ dw,
                                 int n_total, int HW, int C) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const int L = HW * C;
   if (l >= L) return;
   const int hw = l / C, c = l - hw * C;
-  const float wv = w[c * HW + hw];
+  const float wv = wt[l];
   float acc = 0.f;
   for (int n = 0; n < n_total; ++n) {
     const float d = dlogit[n];
@@ -500,7 +548,7 @@ extern "C" int mdgan_bn_forward(const float* x, float* out, const float* gamma, 
   const int row_lanes = 256 / (C / 4);
   bn_partial_kernel<<<G * cpg, 256, row_lanes * 2 * C * sizeof(float), st>>>(x, workspace, Pg, C, cpg, rpc);
   MDGAN_CHECK_LAUNCH();
-  bn_finalize_kernel<<<blocks_for(C, 128), 128, 0, st>>>(workspace, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<blocks_for(C, 32), 32 * kFinLanes, 0, st>>>(workspace, gamma, beta, running_mean, running_var,
                                                          num_batches_tracked, stats, G, Pg, C, cpg, eps, momentum);
   MDGAN_CHECK_LAUNCH();
   const long long total4 = (long long)G * Pg * C / 4;
@@ -521,7 +569,7 @@ extern "C" int mdgan_bn_backward(const float* da, const float* x, const float* s
   bn_bwd_partial_kernel<<<G * cpg, 256, row_lanes * 2 * C * sizeof(float), st>>>(da, x, stats, workspace, Pg, C, cpg,
                                                                                rpc, act, slope);
   MDGAN_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<blocks_for(C, 128), 128, 0, st>>>(workspace, sums, dgamma, dbeta, G, C, cpg);
+  bn_bwd_finalize_kernel<<<blocks_for(C, 32), 32 * kFinLanes, 0, st>>>(workspace, sums, dgamma, dbeta, G, C, cpg);
   MDGAN_CHECK_LAUNCH();
   const long long total4 = (long long)G * Pg * C / 4;
   bn_bwd_apply_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(da, x, stats, sums, dx, Pg, C, total4, act, slope,
@@ -546,24 +594,30 @@ extern "C" int mdgan_tanh_backward(const float* s, const float* x, float* out, l
   return 0;
 }
 
-extern "C" int mdgan_head_forward(const float* a, const float* w, const float* label, float* prob, float* loss_terms,
+extern "C" int mdgan_head_pack(const float* w, float* wt, int HW, int C, void* stream) {
+  if (!w || !wt || HW <= 0 || C <= 0) return MDGAN_ERR_BAD_ARG;
+  head_pack_kernel<<<blocks_for((long long)HW * C, 256), 256, 0, (cudaStream_t)stream>>>(w, wt, HW, C);
+  MDGAN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mdgan_head_forward(const float* a, const float* wt, const float* label, float* prob, float* loss_terms,
                                   float* dlogit, float* loss, int G, int b, int HW, int C, void* stream) {
-  if (!a || !w || !label || !prob || !loss_terms || !dlogit || !loss) return MDGAN_ERR_BAD_ARG;
+  if (!a || !wt || !label || !prob || !loss_terms || !dlogit || !loss) return MDGAN_ERR_BAD_ARG;
   if (C % 4 != 0) return MDGAN_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_total = G * b;
-  head_fwd_kernel<<<blocks_for((long long)n_total * 32, 256), 256, 0, st>>>(a, w, label, prob, loss_terms, dlogit,
-                                                                            n_total, b, HW, C);
+  head_fwd_kernel<<<n_total, 256, 0, st>>>(a, wt, label, prob, loss_terms, dlogit, n_total, b, HW * C);
   MDGAN_CHECK_LAUNCH();
   head_loss_kernel<<<1, 256, 0, st>>>(loss_terms, loss, G, b);
   MDGAN_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int mdgan_head_backward(const float* a, const float* w, const float* dlogit, float* da, float* dw,
+extern "C" int mdgan_head_backward(const float* a, const float* wt, const float* dlogit, float* da, float* dw,
                                    int n_total, int HW, int C, void* stream) {
-  if (!a || !w || !dlogit || !da) return MDGAN_ERR_BAD_ARG;
-  head_bwd_kernel<<<blocks_for((long long)HW * C, 128), 128, 0, (cudaStream_t)stream>>>(a, w, dlogit, da, dw, n_total,
+  if (!a || !wt || !dlogit || !da) return MDGAN_ERR_BAD_ARG;
+  head_bwd_kernel<<<blocks_for((long long)HW * C, 128), 128, 0, (cudaStream_t)stream>>>(a, wt, dlogit, da, dw, n_total,
                                                                                        HW, C);
   MDGAN_CHECK_LAUNCH();
   return 0;

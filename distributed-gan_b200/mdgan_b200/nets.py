@@ -161,6 +161,7 @@ class DiscNet:
                 self.partial.append(torch.empty(ops.thin_wgrad_slices(nmax, Ho, Ho) * Cc * ly.c_in * 16, **f))
         self.bn_ws = torch.empty(max(ws, 1), **f)
         head = L[-1]
+        self.w_head = torch.empty(head.k * head.k * head.c_in, **f)
         self.prob = torch.zeros(nmax, **f)
         self.loss_terms = torch.zeros(nmax, **f)
         self.dlogit = torch.zeros(nmax, **f)
@@ -178,6 +179,7 @@ class DiscNet:
             ops.pack_up(P[ly.weight], self.wq[l])
             if l >= 1:
                 ops.pack_down(P[ly.weight], self.wp[l])
+        ops.head_pack(P[self.L[-1].weight], self.w_head)
 
     def adam(self) -> None:
         s = self.state
@@ -203,7 +205,7 @@ class DiscNet:
                            G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope,
                            round_tf32=(self.rnd and L[l + 1].kind == "down"), eps=bn.eps, momentum=bn.momentum)
         head = L[-1]
-        ops.head_forward(self.a[-1][:n], P[head.weight], labels, self.prob, self.loss_terms, self.dlogit, self.loss, G,
+        ops.head_forward(self.a[-1][:n], self.w_head, labels, self.prob, self.loss_terms, self.dlogit, self.loss, G,
                          b, head.k * head.k, head.c_in)
 
     def backward(self, img: torch.Tensor, G: int, train: bool, out: Optional[torch.Tensor] = None,
@@ -214,7 +216,7 @@ class DiscNet:
         n = G * b
         L = self.L
         head = L[-1]
-        ops.head_backward(self.a[-1][:n], P[head.weight], self.dlogit, self.da[-1][:n],
+        ops.head_backward(self.a[-1][:n], self.w_head, self.dlogit, self.da[-1][:n],
                           Gd[head.weight] if train else None, n, head.k * head.k, head.c_in)
         for l in range(len(L) - 2, 0, -1):
             ly = L[l]

@@ -233,6 +233,13 @@ def tanh_backward(s, x, out, scale: float):
 
 
 # ----------------------------------------------------------------------------- head / loss / optimiser
+def head_pack(w, wt):
+    """w PyTorch [1, C, k, k] -> wt [k*k, C] (the NHWC order of the activations)."""
+    Cc, HW = w.shape[1], w.shape[2] * w.shape[3]
+    _run("head_pack", 1, 0, 8.0 * w.numel(), lambda: _lib.load().mdgan_head_pack(_ptr(w), _ptr(wt), HW, Cc, _stream()))
+    return wt
+
+
 def head_forward(a, w, label, prob, loss_terms, dlogit, loss, G, b, HW, Cc):
     _run("head_forward", 2, 2.0 * G * b * HW * Cc, 4.0 * (G * b * HW * Cc + HW * Cc),
          lambda: _lib.load().mdgan_head_forward(_ptr(a), _ptr(w), _ptr(label), _ptr(prob), _ptr(loss_terms),

@@ -116,13 +116,15 @@ int mdgan_act_backward(const float* da, const float* a, float* dz, long long n, 
 int mdgan_tanh_backward(const float* s, const float* x, float* out, long long n, float scale, void* stream);
 
 /* ---- discriminator head: Conv2d(C,1,k,1,0) on a kxk map + Sigmoid + BCELoss -----------------------------------
- * a NHWC [G*b][HW][C], w PyTorch [1][C][k][k], label[g] in {0,1}.  prob/loss_terms/dlogit are [G*b];
+ * a NHWC [G*b][HW][C]; wt [HW][C] = the PyTorch weight [1][C][k][k] re-ordered by mdgan_head_pack (once per
+ * optimiser step); label[g] in {0,1}; dw is written in the PyTorch layout.  prob/loss_terms/dlogit are [G*b];
  * loss[g] = mean BCE of pass g (log clamped at -100), loss[G] = sum over passes.  dlogit already contains 1/b and
  * BCELoss' max(p(1-p), 1e-12) guard.
  * Replaces CIFAR10.py:96-97,106 / CelebA.py:91-93,100-101 and nn.BCELoss actors/worker.py:96,199-204,222-227. */
-int mdgan_head_forward(const float* a, const float* w, const float* label, float* prob, float* loss_terms,
+int mdgan_head_pack(const float* w, float* wt, int HW, int C, void* stream);
+int mdgan_head_forward(const float* a, const float* wt, const float* label, float* prob, float* loss_terms,
                        float* dlogit, float* loss, int G, int b, int HW, int C, void* stream);
-int mdgan_head_backward(const float* a, const float* w, const float* dlogit, float* da, float* dw, int n_total, int HW,
+int mdgan_head_backward(const float* a, const float* wt, const float* dlogit, float* da, float* dw, int n_total, int HW,
                         int C, void* stream);
 
 /* ---- torch.optim.Adam on a flat parameter buffer (actors/server.py:111-113,308-312; actors/worker.py:97-99,206).

@@ -204,9 +204,10 @@ def test_head_bce(ops, dev, C, k):
     prob, terms, dlogit = (torch.zeros(G * b, device=dev) for _ in range(3))
     loss = torch.zeros(G + 1, device=dev)
     a_d = nhwc(a).to(dev)
-    ops.head_forward(a_d, w.to(dev), labels.to(dev), prob, terms, dlogit, loss, G, b, k * k, C)
+    wt = ops.head_pack(w.to(dev), torch.empty(k * k * C, device=dev))
+    ops.head_forward(a_d, wt, labels.to(dev), prob, terms, dlogit, loss, G, b, k * k, C)
     da, dw = torch.empty_like(a_d), torch.empty_like(w, device=dev)
-    ops.head_backward(a_d, w.to(dev), dlogit, da, dw, G * b, k * k, C)
+    ops.head_backward(a_d, wt, dlogit, da, dw, G * b, k * k, C)
     assert relerr(prob, p) < 1e-5
     assert relerr(loss[:G], torch.stack(losses)) < 1e-5 and relerr(loss[G], sum(losses)) < 1e-5
     assert relerr(nchw(da), ad.grad) < 1e-4 and relerr(dw, wd.grad) < 1e-4
