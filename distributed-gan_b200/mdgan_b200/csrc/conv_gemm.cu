@@ -42,6 +42,7 @@ struct ConvGemmParams {
   int round_tf32;     // 1: store outputs rounded to TF32 (they feed another tensor-core operand)
   int accumulate;     // 1: dst += result (NCHW outputs only; sums feedbacks of workers sharing a batch)
   int lo_row_offset;  // tf32x3: row offset of the `lo` half of the packed weights
+  int dbg;            // bottleneck probes (tools/conv_bench.py): 1 skip split, 2 skip gathers, 4 skip MMAs; results invalid
 };
 
 constexpr int kBM = 128;
@@ -163,13 +164,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
         const bool ok = row_ok[i] && sh >= 0 && sh < p.Hs && sw >= 0 && sw < p.Ws;
         const float* g = p.src + (ok ? (base_off[i] + tap_off) : 0);
         const uint32_t d = a_stage + r * 128 + ((chunk ^ (r & 7)) << 4);
-        cp_async_16(d, g, ok ? 16u : 0u);
+        if (!(p.dbg & 2)) cp_async_16(d, g, ok ? 16u : 0u);
       }
       cp_async_commit();
       if (it >= LAG) {
         cp_async_wait<LAG>();
         const int sd = (it - LAG) % STAGES;
-        if (X3) {
+        if (X3 && !(p.dbg & 1)) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = row_in + 32 * i;
@@ -184,7 +185,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
     cp_async_wait<0>();
     for (int it = (ksteps > LAG ? ksteps - LAG : 0); it < ksteps; ++it) {
       const int sd = it % STAGES;
-      if (X3) {
+      if (X3 && !(p.dbg & 1)) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = row_in + 32 * i;
@@ -288,6 +289,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
         const uint32_t b_addr = a_addr + S::kABytes;
 #pragma unroll
         for (int k = 0; k < kBK / 8; ++k) {
+          if (p.dbg & 4) break;
           const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
           if (X3) {
@@ -314,6 +316,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
   }
 }
 
+static int g_conv_dbg = 0;
+
 template <int BN, int STAGES, bool X3>
 static int launch_conv_gemm(const CUtensorMap& tmap, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
   using S = ConvGemmSmem<BN, STAGES, X3>;
@@ -332,6 +336,8 @@ static int launch_conv_gemm(const CUtensorMap& tmap, const ConvGemmParams& p, di
 
 using namespace mdgan;
 
+extern "C" void mdgan_debug_set_conv_flags(int flags) { g_conv_dbg = flags; }
+
 // See include/mdgan_b200.h for the contract.
 extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img,
                                int Hg, int Wg, int Hs, int Ws, int C, int mode, int N, int N_pad, int out_nchw,
@@ -346,6 +352,7 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   p.M = n_img * Hg * Wg;
   p.round_tf32 = round_tf32;
   p.accumulate = accumulate;
+  p.dbg = g_conv_dbg;
   if (accumulate && !out_nchw) return MDGAN_ERR_UNSUPPORTED;
   if (p.M <= 0) return MDGAN_ERR_BAD_ARG;
   const int taps = mode == 0 ? 16 : (mode == 1 ? 4 : 1);
