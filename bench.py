@@ -336,10 +336,7 @@ def run_ours(args) -> None:
         flush.zero_()                 # evict L2 between timed iterations (outside the per-step event pair)
         engine.stage_inputs()         # device-to-device: next resident real batch into the step's input buffer
         ev[i][0].record()
-        if graphed:
-            engine.graph.replay()
-        else:
-            engine.device_iteration()
+        engine.device_iteration()     # graph replay (or eager launches with --no-graph)
         ev[i][1].record()
     sync_all()
     clocks = sampler.stop() if rank == 0 else None

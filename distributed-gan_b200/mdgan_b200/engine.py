@@ -102,14 +102,19 @@ class MDGANEngine:
         self.d_loss = torch.zeros((len(self.local), max(cfg.local_epochs, 1)), **f)
         self.g_loss = torch.zeros((len(self.local),), **f)
         self.last_pairs: Optional[torch.Tensor] = None
+        self.graph = None
+        self._uploaded = None
         self.iterations_done = 0
 
     # ------------------------------------------------------------------------------------------ phases
     def stage_inputs(self) -> None:
-        """Host half of an iteration: everything that touches host RNG / host memory and therefore cannot live in
-        the captured CUDA graph.  server.py:219 -- in parity mode (z_source == "host") the noise consumes process
-        0's global torch RNG exactly like the reference; real batches come from the host loaders in reference
-        order (worker.py:162-167).  Fills pinned staging buffers only; the device copies are in the device half."""
+        """Host half of an iteration: everything that touches host RNG / host memory.  server.py:219 -- in parity
+        mode (z_source == "host") the noise consumes process 0's global torch RNG exactly like the reference; real
+        batches come from the host loaders in reference order (worker.py:162-167).  Fills the pinned staging buffers,
+        after making sure the previous iteration's uploads have read them (the host may run iterations ahead of the
+        GPU: nothing else in the loop synchronises)."""
+        if self._uploaded is not None:
+            self._uploaded.synchronize()
         kb = self.k * self.b
         if self.proc == 0 and self.cfg.z_source == "host":
             self.z_host.copy_(torch.randn((kb, self.cfg.z_dim, 1, 1)).view(kb, self.cfg.z_dim))
@@ -118,17 +123,28 @@ class MDGANEngine:
             if stage is not None:
                 stage()
 
-    def draw_noise(self) -> None:
-        if self.cfg.z_source == "host":
+    def upload_inputs(self) -> None:
+        """Pinned staging -> device (async copies on the compute stream, always launched eagerly so that an event can
+        mark the moment the staging buffers are free again)."""
+        if self.proc == 0 and self.cfg.z_source == "host":
             self.z.copy_(self.z_host, non_blocking=True)
-        else:
-            self.z.normal_()
+        for n in self.local:
+            upload = getattr(self.real_sources[n], "upload", None)
+            if upload is not None:
+                upload()
+        if self.device.type == "cuda":
+            if self._uploaded is None:
+                self._uploaded = torch.cuda.Event()
+            self._uploaded.record()
 
     def generate(self, staged: bool = False) -> None:
+        """staged=False: also runs the host staging and the uploads (one call per phase, as the actors use it)."""
         if not staged:
             self.stage_inputs()
+            self.upload_inputs()
         if self.proc == 0:
-            self.draw_noise()
+            if self.cfg.z_source != "host":
+                self.z.normal_()
             X = self.gen.forward(self.z)
             if X.data_ptr() != self.X.data_ptr():
                 self.X = X  # the net owns the [k*b, C, H, W] output buffer; broadcast straight out of it
@@ -165,11 +181,19 @@ class MDGANEngine:
         self.last_pairs = pairs
         return pairs
 
-    def device_iteration(self) -> None:
-        """Device half: H2D of the staged inputs, G forward, exchange, D steps + feedback, reduce, G backward, Adam."""
+    def compute_iteration(self) -> None:
+        """G forward, exchange, D steps + feedback, reduce, G backward, Adam: device work only, graph-capturable."""
         self.generate(staged=True)
         self.train_workers()
         self.update_generator()
+
+    def device_iteration(self) -> None:
+        """Device half of an iteration: uploads (eager) + the compute part (the captured graph if there is one)."""
+        self.upload_inputs()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.compute_iteration()
 
     def capture(self) -> None:
         """Capture the device half of the steady-state iteration into one CUDA graph (at b <= 128 the
@@ -180,15 +204,19 @@ class MDGANEngine:
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.device_iteration()
+            self.compute_iteration()
         self.graph = graph
+
+    def close(self) -> None:
+        """Release the captured graph.  Must happen before the process group is destroyed: tearing down an NCCL
+        communicator that a live CUDA graph still references hangs (observed on 2 x B200, NCCL 2.28.9)."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        self.graph = None
 
     def iteration(self, epoch: int) -> None:
         self.stage_inputs()
-        if getattr(self, "graph", None) is not None:
-            self.graph.replay()
-        else:
-            self.device_iteration()
+        self.device_iteration()
         self.maybe_swap(epoch)
         self.iterations_done += 1
 

@@ -30,6 +30,14 @@ class Exchange:
         self.proc, self.n_procs, self.n_workers = proc, n_procs, n_workers
         if n_procs > 1 and not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised before building a multi-process Exchange")
+        # The per-iteration collectives (C3, C4) run on the default group and may be captured into a CUDA graph; the
+        # rare, host-driven swap traffic gets its own communicators so that eager operations never interleave with
+        # graph-captured ones on one NCCL communicator: a host-side (gloo) group for the pair table, which is host
+        # data anyway, and a second device group for the state exchange.
+        self.ctl_group = self.swap_group = None
+        if n_procs > 1:
+            self.ctl_group = dist.new_group(backend="gloo")
+            self.swap_group = dist.new_group()
 
     # ---- C4
     def broadcast_fakes(self, X: torch.Tensor) -> None:
@@ -46,11 +54,11 @@ class Exchange:
         """pairs: [N/2, 2] int32 host tensor on process 0 (None elsewhere); returns it on every process (host)."""
         if self.n_procs == 1:
             return pairs
-        buf = torch.zeros((self.n_workers // 2, 2), dtype=torch.int32, device=device)
+        buf = torch.zeros((self.n_workers // 2, 2), dtype=torch.int32)
         if self.proc == 0:
             buf.copy_(pairs)
-        dist.broadcast(buf, src=0)
-        return buf.cpu()
+        dist.broadcast(buf, src=0, group=self.ctl_group)
+        return buf
 
     # ---- C6
     def swap_states(self, local_states: Dict[int, Tuple[torch.Tensor, torch.Tensor]], pairs: torch.Tensor) -> List[int]:
@@ -76,10 +84,10 @@ class Exchange:
             peer = routing.process_of_worker(pn, self.n_procs, self.n_workers)
             rf, ri = torch.empty_like(f32), torch.empty_like(i64)
             # message order between two processes: by the SENDING worker's index on both sides
-            ops.append((n, dist.P2POp(dist.isend, f32, peer)))
-            ops.append((n, dist.P2POp(dist.isend, i64, peer)))
-            ops.append((pn, dist.P2POp(dist.irecv, rf, peer)))
-            ops.append((pn, dist.P2POp(dist.irecv, ri, peer)))
+            ops.append((n, dist.P2POp(dist.isend, f32, peer, group=self.swap_group)))
+            ops.append((n, dist.P2POp(dist.isend, i64, peer, group=self.swap_group)))
+            ops.append((pn, dist.P2POp(dist.irecv, rf, peer, group=self.swap_group)))
+            ops.append((pn, dist.P2POp(dist.irecv, ri, peer, group=self.swap_group)))
             copies.append((f32, rf, i64, ri))
             changed.append(n)
         if ops:

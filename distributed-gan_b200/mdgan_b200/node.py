@@ -53,9 +53,11 @@ class _DeviceBatches:
         """Host half: next batch of the reference-order loader into the pinned buffer."""
         self.pinned.copy_(self.stream.next())
 
-    def __call__(self) -> torch.Tensor:
-        """Device half (graph-capturable): H2D from the pinned buffer."""
+    def upload(self) -> None:
+        """H2D from the pinned buffer (async on the current stream)."""
         self.dev.copy_(self.pinned, non_blocking=True)
+
+    def __call__(self) -> torch.Tensor:
         return self.dev
 
 
@@ -163,8 +165,13 @@ def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: 
             torch.cuda.synchronize(device)
         return time.time()
 
+    # Steady state runs as one CUDA graph per iteration (captured after two eager iterations); MDGAN_GRAPH=0 or
+    # MDGAN_SYNC_TIMING=1 (per-phase device-synchronised CSV spans) keep the eager phase-by-phase launches.
+    use_graph = os.environ.get("MDGAN_GRAPH", "1") == "1" and not sync_timing
     FID, IS = _maybe_metrics()
     for epoch in range(epochs):
+        if use_graph and epoch == 2:
+            engine.capture()
         t0 = stamp()
         srow = {c: None for c in SERVER_COLUMNS}
         srow.update({"epoch": epoch, "start.epoch": t0, "start.epoch_calculation": t0, "swap": False,
@@ -175,17 +182,25 @@ def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: 
             wrows[n].update({"epoch": epoch, "start.epoch": t0, "size.model": model_mb[n],
                              "size.sent": img_bytes / _MB, "size.recv": 2 * img_bytes / _MB})
         srow["start.generate_data"] = t0
-        engine.generate()
-        t1 = stamp()
+        if engine.graph is None:
+            engine.generate()
+            t1 = stamp()
+        else:
+            engine.stage_inputs()
+            t1 = stamp()
         srow["end.generate_data"] = srow["start.send_data"] = srow["end.send_data"] = srow["start.recv_data"] = t1
         for n in local:
             wrows[n]["start.recv_data"], wrows[n]["end.recv_data"], wrows[n]["start.calc_gradients"] = t0, t1, t1
-        engine.train_workers()
+        if engine.graph is None:
+            engine.train_workers()
+        else:
+            engine.device_iteration()   # uploads + the captured G forward / D steps / feedback / G backward / Adam
         t2 = stamp()
         srow["end.recv_data"] = srow["start.agg_gradients"] = t2
         for n in local:
             wrows[n]["end.calc_gradients"] = wrows[n]["start.send"] = wrows[n]["end.send"] = wrows[n]["end.epoch"] = t2
-        engine.update_generator()
+        if engine.graph is None:
+            engine.update_generator()
         t3 = stamp()
         srow["end.agg_gradients"] = srow["start.calc_gradients"] = srow["end.calc_gradients"] = t3
         pairs = engine.maybe_swap(epoch)
@@ -231,6 +246,7 @@ def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: 
 
     torch.cuda.synchronize(device)
     engine.sync_modules()
+    engine.close()
     if proc == 0:
         weights_dir.mkdir(parents=True, exist_ok=True)
         torch.save(generator.state_dict(), weights_dir / "generator_final.pt")

@@ -1,0 +1,87 @@
+"""The reference-facing entry points on a GPU: bootstrap.py (server + workers through actors.server.start) and
+standalone_gan.py, run with the reference's flags on synthetic data, checked against the oracle and for the
+reference's output files (CSV schemas, weight files with the reference's state_dict keys)."""
+import csv
+import os
+
+import pytest
+import torch
+
+from parity import FREE_TOL, l2err
+from util import plugin
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bootstrap_single_gpu_matches_oracle(tmp_path, monkeypatch):
+    import bootstrap
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200.node import SERVER_COLUMNS, WORKER_COLUMNS
+    from oracle.mdgan_oracle import OracleMDGAN
+
+    N, b, epochs, m = 2, 8, 5, 2 * 4 * 8
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("MDGAN_PRECISION", "tf32x3")
+    bootstrap.main(["--backend", "nccl", "--world_size", str(N + 1), "--ranks", f"0..{N}", "--dataset", "CIFAR10",
+                    "--epochs", str(epochs), "--local_epochs", "1", "--swap_interval", "2", "--device", "cuda",
+                    "--batch_size", str(b), "--iid", "1", "--seed", "3", "--beta_1", "0.5", "--generator_lr", "0.0002",
+                    "--discriminator_lr", "0.0002", "--log_interval", "1000", "--gpus", "1", "--synthetic", str(m)])
+    monkeypatch.delenv("MDGAN_SYNTH_M", raising=False)
+    mod = plugin("CIFAR10")
+    oracle = OracleMDGAN(mod.Generator, mod.Discriminator, SyntheticImages(mod.SHAPE, m), N, b, mod.Z_DIM, mod.SHAPE,
+                         seed=3, beta_1=0.5, swap_interval=2)
+    ref = [oracle.step(e, record=False) for e in range(epochs)]
+
+    g = torch.load(tmp_path / "weights" / "generator_final.pt")
+    assert list(g.keys()) == list(oracle.G.state_dict().keys())
+    flat = lambda sd: torch.cat([v.reshape(-1).double() for k, v in sd.items() if v.dtype == torch.float32 and "running" not in k])
+    assert l2err(flat(g), flat(oracle.G.state_dict())) <= FREE_TOL["weights_l2"]
+    for n in range(N):
+        d = torch.load(tmp_path / "weights" / f"worker_{n + 1}" / "discriminator.pth")
+        rd = oracle.D[n].state_dict()
+        assert list(d.keys()) == list(rd.keys())
+        assert l2err(flat(d), flat(rd)) <= FREE_TOL["weights_l2"]
+        assert all(int(d[k]) == int(rd[k]) == 3 * epochs for k in d if k.endswith("num_batches_tracked"))
+        rows = list(csv.DictReader(open(tmp_path / "logs" / f"mdgan.{N}.CIFAR10.worker.{n + 1}.logs.csv")))
+        assert list(rows[0].keys()) == WORKER_COLUMNS and len(rows) == epochs
+        for e, row in enumerate(rows):
+            assert abs(float(row["mean_d_loss"]) - ref[e]["mean_d_loss"][n]) <= FREE_TOL["loss"] * abs(ref[e]["mean_d_loss"][n])
+            partner = None
+            if ref[e]["pairs"] is not None:
+                pairs = {a: c for a, c in ref[e]["pairs"].tolist()}
+                pairs.update({c: a for a, c in ref[e]["pairs"].tolist()})
+                partner = pairs[n + 1]
+            assert (row["swap_with"] == "" and partner is None) or int(row["swap_with"]) == partner
+        assert float(rows[0]["size.model"]) == 2.5332183837890625
+    srows = list(csv.DictReader(open(tmp_path / "logs" / f"mdgan.{N}.CIFAR10.server.logs.csv")))
+    assert list(srows[0].keys()) == SERVER_COLUMNS and len(srows) == epochs
+    assert [r["swap"] for r in srows] == ["False", "False", "True", "False", "True"]
+    assert (tmp_path / "saved_images" / "real_images.png").exists()
+    assert (tmp_path / "saved_images" / f"generated_epoch_{epochs - 1}.png").exists()
+
+
+def test_standalone_matches_oracle(tmp_path, monkeypatch):
+    import standalone_gan
+    from datasets.DataPartitioner import SyntheticImages
+    from oracle.mdgan_oracle import OracleStandalone
+
+    b, epochs, m = 16, 3, 64
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("MDGAN_SYNTH_M", str(m))
+    standalone_gan.main(["--dataset", "CIFAR10", "--epochs", str(epochs), "--local_epochs", "1", "--batch_size", str(b),
+                         "--device", "cuda", "--seed", "1", "--beta_1", "0.5", "--log_interval", "1000"])
+    mod = plugin("CIFAR10")
+    oracle = OracleStandalone(mod.Generator, mod.Discriminator, SyntheticImages(mod.SHAPE, m), b, mod.Z_DIM, seed=1,
+                              beta_1=0.5)
+    ref = [oracle.step() for _ in range(epochs)]
+    rows = list(csv.DictReader(open(tmp_path / "logs" / "CIFAR10.standalone.logs.csv")))
+    assert len(rows) == epochs
+    for row, r in zip(rows, ref):
+        assert abs(float(row["mean_d_loss"]) - r["mean_d_loss"]) <= FREE_TOL["loss"] * abs(r["mean_d_loss"])
+        assert abs(float(row["mean_g_loss"]) - r["mean_g_loss"]) <= FREE_TOL["loss"] * abs(r["mean_g_loss"])
+    g = torch.load(tmp_path / "weights" / f"netG_epoch_{epochs - 1}.pth")
+    d = torch.load(tmp_path / "weights" / f"netD_epoch_{epochs - 1}.pth")
+    flat = lambda sd: torch.cat([v.reshape(-1).double() for k, v in sd.items() if v.dtype == torch.float32 and "running" not in k])
+    assert list(g.keys()) == list(oracle.G.state_dict().keys()) and list(d.keys()) == list(oracle.D.state_dict().keys())
+    assert l2err(flat(g), flat(oracle.G.state_dict())) <= FREE_TOL["weights_l2"]
+    assert l2err(flat(d), flat(oracle.D.state_dict())) <= FREE_TOL["weights_l2"]
