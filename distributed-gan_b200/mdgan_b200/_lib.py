@@ -24,7 +24,6 @@ SIGNATURES = {
     "mdgan_wgrad_splits": (_i, [_i, _i, _i, _i, _i, _i]),
     "mdgan_wgrad_gemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_debug_set_wgrad_desc": (None, [_i, _i]),
-    "mdgan_debug_set_conv_flags": (None, [_i]),
     "mdgan_pack_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_wgrad_unpack": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_reduce_slices": (_i, [_p, _p, _i, _ll, _p]),

@@ -42,13 +42,13 @@ struct ConvGemmParams {
   int round_tf32;     // 1: store outputs rounded to TF32 (they feed another tensor-core operand)
   int accumulate;     // 1: dst += result (NCHW outputs only; sums feedbacks of workers sharing a batch)
   int lo_row_offset;  // tf32x3: row offset of the `lo` half of the packed weights
-  int dbg;            // bottleneck probes (tools/conv_bench.py): 1 skip split, 2 skip gathers, 4 skip MMAs; results invalid
 };
 
 constexpr int kBM = 128;
 constexpr int kBK = 32;  // fp32 elements per K step = 128 bytes
 constexpr int kNumProducerWarps = 8;
 constexpr int kThreads = (kNumProducerWarps + 2) * 32;
+constexpr int kPrefetch = 4;  // K steps of activation loads kept in flight in registers per producer thread
 
 template <int BN, int STAGES, bool X3>
 struct ConvGemmSmem {
@@ -60,12 +60,15 @@ struct ConvGemmSmem {
   static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
   // tf32x3 keeps several TMEM accumulators: the tensor core adds into its fp32 accumulator with truncation, so a
-  // long accumulation chain drifts by ~4e-8 per add (measured: 1.5e-5 at K = 4096 with one accumulator).  The
-  // hi*hi products are dealt round-robin over kMain accumulators, the two small correction products go to their
-  // own accumulator, and the epilogue sums them with ordinary (round-to-nearest) fp32 adds.
-  static constexpr int kAccs = X3 ? (512 / BN > 16 ? 16 : 512 / BN) : 1;
-  static constexpr int kMain = X3 ? kAccs - 1 : 1;
-  static constexpr uint32_t kTmemCols = X3 ? (kAccs * BN < 32 ? 32 : kAccs * BN) : (BN < 32 ? 32 : BN);
+  // long accumulation chain drifts by ~3e-8 per add (measured: 1.5e-5 at K = 4096 with one accumulator).  The four
+  // K=8 slices of a K step go to kMain accumulators (slice k -> accumulator k % kMain, a compile-time constant in
+  // the unrolled issue loop), the two small correction products to their own accumulator, and the epilogue sums
+  // them with ordinary (round-to-nearest) fp32 adds.
+  static constexpr int kMain = X3 ? (BN > 64 ? 2 : 4) : 1;
+  static constexpr int kAccs = X3 ? kMain + 1 : 1;
+  static constexpr uint32_t kTmemCols = kAccs * BN <= 32 ? 32 : kAccs * BN <= 64 ? 64 : kAccs * BN <= 128 ? 128
+                                        : kAccs * BN <= 256 ? 256 : 512;
+  static_assert(kAccs * BN <= 512, "TMEM holds 512 columns");
 };
 
 __device__ __forceinline__ float round_to_tf32(float x) {
@@ -74,25 +77,14 @@ __device__ __forceinline__ float round_to_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// In-place split of one 16-byte chunk: smem[hi_addr] <- hi = tf32(x), smem[hi_addr + lo_delta] <- lo = tf32(x - hi).
-__device__ __forceinline__ void split_chunk_x3(uint32_t hi_addr, uint32_t lo_delta) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi_addr));
-  // hi = x rounded to nearest TF32 (so the tensor core's truncation of hi is exact and the split is unbiased);
-  // lo = (x - hi) rounded to nearest TF32.  |lo| <= 2^-11 |x|, and the dropped lo*lo term is ~2^-22 relative.
-  float4 h, l;
-  h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-  l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr + lo_delta), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
-               : "memory");
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 template <int BN, int STAGES, bool X3>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParams p) {
   using S = ConvGemmSmem<BN, STAGES, X3>;
-  constexpr int LAG = STAGES - 2;  // cp.async groups kept in flight per producer thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
@@ -128,14 +120,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
 
   if (warp < kNumProducerWarps) {
     // ------------------------------------------------------------------ A producers
-    const int chunk = threadIdx.x & 7;   // 16-byte chunk within the 128-byte row
-    const int row_in = threadIdx.x >> 3; // 0..31
+    // Each thread owns the 16-byte chunk `chunk` of rows row_in + 32 i.  Loads go global -> registers, kPrefetch K
+    // steps ahead (their latency never sits on the critical path), are rounded / split into TF32 hi and lo parts in
+    // registers and stored once to the swizzled stage -- one shared-memory pass per operand.
+    const int chunk = threadIdx.x & 7;
+    const int row_in = threadIdx.x >> 3;  // 0..31
     const int SI = (p.mode == 0) ? 2 : 1;
     int base_off[4], sh0[4], sw0[4];
     bool row_ok[4];
+    uint32_t soff[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int m = m0 + row_in + 32 * i;
+      const int r = row_in + 32 * i;
+      const int m = m0 + r;
       row_ok[i] = m < p.M;
       const int mm = row_ok[i] ? m : 0;
       const int img = mm / (p.Hg * p.Wg);
@@ -144,56 +141,53 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
       sh0[i] = gi * SI;
       sw0[i] = gj * SI;
       base_off[i] = ((img * p.Hs + sh0[i]) * p.Ws + sw0[i]) * p.C + chunk * 4;
+      soff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
     }
     const uint32_t a_smem0 = smem_u32(smem);
-    int tap = 0, cc = 0;
-    for (int it = 0; it < ksteps; ++it) {
-      const int s = it % STAGES;
-      const uint32_t par = (it / STAGES) & 1;
-      mbar_wait(&empty_bar[s], par ^ 1);
+    int tap_l = 0, cc_l = 0;  // coordinates of the next K step to load
+    auto issue_loads = [&](float4(&buf)[4]) {
       int dh, dw;
-      if (p.mode == 0) { dh = (tap >> 2) - 1; dw = (tap & 3) - 1; }
-      else if (p.mode == 1) { dh = ph - (tap >> 1); dw = pw - (tap & 1); }
+      if (p.mode == 0) { dh = (tap_l >> 2) - 1; dw = (tap_l & 3) - 1; }
+      else if (p.mode == 1) { dh = ph - (tap_l >> 1); dw = pw - (tap_l & 1); }
       else { dh = 0; dw = 0; }
-      const int tap_off = (dh * p.Ws + dw) * p.C + cc * kBK;
-      const uint32_t a_stage = a_smem0 + s * S::kStageBytes;
+      const int tap_off = (dh * p.Ws + dw) * p.C + cc_l * kBK;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int r = row_in + 32 * i;
         const int sh = sh0[i] + dh, sw = sw0[i] + dw;
         const bool ok = row_ok[i] && sh >= 0 && sh < p.Hs && sw >= 0 && sw < p.Ws;
-        const float* g = p.src + (ok ? (base_off[i] + tap_off) : 0);
-        const uint32_t d = a_stage + r * 128 + ((chunk ^ (r & 7)) << 4);
-        if (!(p.dbg & 2)) cp_async_16(d, g, ok ? 16u : 0u);
+        buf[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.src + base_off[i] + tap_off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      cp_async_commit();
-      if (it >= LAG) {
-        cp_async_wait<LAG>();
-        const int sd = (it - LAG) % STAGES;
-        if (X3 && !(p.dbg & 1)) {
+      if (++cc_l == cchunks) { cc_l = 0; ++tap_l; }
+    };
+    float4 buf[kPrefetch][4];
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u)
+      if (u < ksteps) issue_loads(buf[u]);
+    int s = 0;
+    uint32_t par = 0;
+    for (int it0 = 0; it0 < ksteps; it0 += kPrefetch) {
+#pragma unroll
+      for (int u = 0; u < kPrefetch; ++u) {
+        const int it = it0 + u;
+        if (it < ksteps) {
+          mbar_wait(&empty_bar[s], par ^ 1);
+          const uint32_t a_stage = a_smem0 + s * S::kStageBytes;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int r = row_in + 32 * i;
-            split_chunk_x3(a_smem0 + sd * S::kStageBytes + r * 128 + ((chunk ^ (r & 7)) << 4), S::kHalfBytes);
+            const float4 v = buf[u][i];
+            const float hx = tf32_round_fast(v.x), hy = tf32_round_fast(v.y), hz = tf32_round_fast(v.z),
+                        hw = tf32_round_fast(v.w);
+            sts128(a_stage + soff[i], hx, hy, hz, hw);
+            if (X3)  // lo = x - hi (exact in fp32); the tensor core truncates it to TF32 (2^-21 relative to x) and
+                     // the dropped lo*lo term is ~2^-22 relative
+              sts128(a_stage + S::kHalfBytes + soff[i], v.x - hx, v.y - hy, v.z - hz, v.w - hw);
           }
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&full_bar[sd]);
-      }
-      if (++cc == cchunks) { cc = 0; ++tap; }
-    }
-    cp_async_wait<0>();
-    for (int it = (ksteps > LAG ? ksteps - LAG : 0); it < ksteps; ++it) {
-      const int sd = it % STAGES;
-      if (X3 && !(p.dbg & 1)) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = row_in + 32 * i;
-          split_chunk_x3(a_smem0 + sd * S::kStageBytes + r * 128 + ((chunk ^ (r & 7)) << 4), S::kHalfBytes);
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[s]);
+          if (it + kPrefetch < ksteps) issue_loads(buf[u]);
+          if (++s == STAGES) { s = 0; par ^= 1; }
         }
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&full_bar[sd]);
     }
 
     // ------------------------------------------------------------------ epilogue
@@ -219,16 +213,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
         float v[16];
         tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
         if (X3) {
-          const int valid = ksteps * (kBK / 8) < S::kMain ? ksteps * (kBK / 8) : S::kMain;
           float t[16];
-          for (int a = 1; a < valid; ++a) {
+#pragma unroll
+          for (int a = 1; a < S::kAccs; ++a) {
             tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col, t);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += t[j];
           }
-          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + S::kMain * BN + col, t);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += t[j];
         }
         if (!ok) continue;
         const int nbase = n0 + col;
@@ -266,45 +257,49 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
     // ------------------------------------------------------------------ B producer (TMA)
     if (lane == 0) {
       const int row0 = (p.mode == 1 ? phase * p.N_pad : 0) + n0;
+      int s = 0;
+      uint32_t par = 0;
       for (int it = 0; it < ksteps; ++it) {
-        const int s = it % STAGES;
-        const uint32_t par = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], par ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], (X3 ? 2 : 1) * S::kBBytes);
         const uint32_t b_dst = smem_u32(smem + s * S::kStageBytes + S::kABytes);
         tma_load_2d(b_dst, &tmap_w, &full_bar[s], it * kBK, row0);
         if (X3) tma_load_2d(b_dst + S::kHalfBytes, &tmap_w, &full_bar[s], it * kBK, row0 + p.lo_row_offset);
+        if (++s == STAGES) { s = 0; par ^= 1; }
       }
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer
+    // One thread; the loop carries nothing but the stage descriptor and the barrier parity, every other quantity
+    // (K-slice offset inside the swizzle atom, hi/lo offset, accumulator column) is an immediate of the unrolled
+    // body: a tcgen05.mma 128 x BN x 8 costs max(44, BN/2) clk (tools/micro/umma_micro.cu), an issue loop that
+    // rebuilds descriptors or takes a modulo per MMA costs more than that.
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
+      const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      constexpr uint64_t kStageStep = S::kStageBytes >> 4, kBStep = S::kABytes >> 4, kLoStep = S::kHalfBytes >> 4;
+      int s = 0;
+      uint32_t par = 0;
+      uint64_t da0 = desc0;
       for (int it = 0; it < ksteps; ++it) {
-        const int s = it % STAGES;
-        const uint32_t par = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], par);
         tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
-        const uint32_t b_addr = a_addr + S::kABytes;
+        const uint32_t acc = it != 0 ? 1u : 0u;
 #pragma unroll
         for (int k = 0; k < kBK / 8; ++k) {
-          if (p.dbg & 4) break;
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+          const uint64_t da = da0 + 2 * k, db = da + kBStep;
           if (X3) {
-            const uint64_t da_lo = make_smem_desc_sw128(a_addr + S::kHalfBytes + k * 32, 16, 1024);
-            const uint64_t db_lo = make_smem_desc_sw128(b_addr + S::kHalfBytes + k * 32, 16, 1024);
-            const int g = it * (kBK / 8) + k;  // global K-slice counter
             const uint32_t acc_corr = tmem_base + S::kMain * BN;
-            umma_tf32(acc_corr, da_lo, db, idesc, g != 0 ? 1u : 0u);
-            umma_tf32(acc_corr, da, db_lo, idesc, 1u);
-            umma_tf32(tmem_base + (g % S::kMain) * BN, da, db, idesc, g >= S::kMain ? 1u : 0u);
+            umma_tf32(acc_corr, da + kLoStep, db, idesc, k == 0 ? acc : 1u);
+            umma_tf32(acc_corr, da, db + kLoStep, idesc, 1u);
+            umma_tf32(tmem_base + (k % S::kMain) * BN, da, db, idesc, k < S::kMain ? acc : 1u);
           } else {
-            umma_tf32(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_base, da, db, idesc, k == 0 ? acc : 1u);
           }
         }
         umma_commit(&empty_bar[s]);
+        da0 += kStageStep;
+        if (++s == STAGES) { s = 0; par ^= 1; da0 = desc0; }
       }
       umma_commit(tmem_full_bar);
     }
@@ -316,11 +311,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
   }
 }
 
-static int g_conv_dbg = 0;
-
 template <int BN, int STAGES, bool X3>
 static int launch_conv_gemm(const CUtensorMap& tmap, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
   using S = ConvGemmSmem<BN, STAGES, X3>;
+  static_assert(S::kDynamic <= 227 * 1024, "shared memory per CTA");
   static bool configured = false;
   if (!configured) {
     MDGAN_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -332,11 +326,18 @@ static int launch_conv_gemm(const CUtensorMap& tmap, const ConvGemmParams& p, di
   return 0;
 }
 
+// Estimated cycles of one launch for tile width bn: waves of CTAs x K steps x MMA time per K step (four K=8 slices,
+// three MMAs each in tf32x3), a 128 x bn x 8 MMA costing max(44, bn/2) clk, plus a fixed per-CTA prologue/epilogue.
+static double conv_cost(int row_tiles, int phases, int n_pad, int bn, int ksteps, bool x3) {
+  const long ctas = static_cast<long>(row_tiles) * phases * (n_pad / bn);
+  const long waves = (ctas + 147) / 148;
+  const double mma = bn / 2 > 44 ? bn / 2 : 44;
+  return waves * (ksteps * 4.0 * (x3 ? 3 : 1) * mma + 3000.0 + 40.0 * bn);
+}
+
 }  // namespace mdgan
 
 using namespace mdgan;
-
-extern "C" void mdgan_debug_set_conv_flags(int flags) { g_conv_dbg = flags; }
 
 // See include/mdgan_b200.h for the contract.
 extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img,
@@ -352,24 +353,26 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   p.M = n_img * Hg * Wg;
   p.round_tf32 = round_tf32;
   p.accumulate = accumulate;
-  p.dbg = g_conv_dbg;
   if (accumulate && !out_nchw) return MDGAN_ERR_UNSUPPORTED;
   if (p.M <= 0) return MDGAN_ERR_BAD_ARG;
   const int taps = mode == 0 ? 16 : (mode == 1 ? 4 : 1);
   const int phases = mode == 1 ? 4 : 1;
   const int row_tiles = ceil_div(p.M, kBM);
-  // Tile width: widest BN that divides N_pad, narrowed while the grid would leave most of the 148 SMs idle.
-  int bn = 16;
-  for (int c : {128, 64, 32})
-    if (N_pad % c == 0) { bn = c; break; }
-  while (bn > 32 && row_tiles * phases * (N_pad / bn) < 148 && N_pad % (bn / 2) == 0) bn /= 2;
-  if (precision == 1 && bn > 64) bn = 64;  // tf32x3: leave TMEM room for >= 7 main accumulators
-  if (force_bn > 0) {
-    if (N_pad % force_bn != 0 || (precision == 1 && force_bn > 64)) return MDGAN_ERR_BAD_ARG;
-    bn = force_bn;
-  }
   if (precision != 0 && precision != 1) return MDGAN_ERR_BAD_ARG;
   const bool x3 = precision == 1;
+  // Tile width: the candidate (dividing N_pad) with the lowest estimated time -- wide tiles use the tensor core
+  // better, narrow ones fill the 148 SMs when the row grid is small.
+  int bn = 16;
+  double best = 1e300;
+  for (int c : {128, 64, 32, 16}) {
+    if (N_pad % c != 0) continue;
+    const double t = conv_cost(row_tiles, phases, N_pad, c, taps * (C / kBK), x3);
+    if (t < best) { best = t; bn = c; }
+  }
+  if (force_bn > 0) {
+    if (N_pad % force_bn != 0) return MDGAN_ERR_BAD_ARG;
+    bn = force_bn;
+  }
   const uint64_t rows = static_cast<uint64_t>(N_pad) * phases;
   p.lo_row_offset = static_cast<int>(rows);
   CUtensorMap tmap;
@@ -378,10 +381,10 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   dim3 grid(row_tiles, N_pad / bn, phases);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 128: return x3 ? MDGAN_ERR_UNSUPPORTED : launch_conv_gemm<128, 6, false>(tmap, p, grid, st);
-    case 64: return x3 ? launch_conv_gemm<64, 4, true>(tmap, p, grid, st) : launch_conv_gemm<64, 4, false>(tmap, p, grid, st);
-    case 32: return x3 ? launch_conv_gemm<32, 4, true>(tmap, p, grid, st) : launch_conv_gemm<32, 4, false>(tmap, p, grid, st);
-    case 16: return x3 ? launch_conv_gemm<16, 4, true>(tmap, p, grid, st) : launch_conv_gemm<16, 4, false>(tmap, p, grid, st);
+    case 128: return x3 ? launch_conv_gemm<128, 3, true>(tmap, p, grid, st) : launch_conv_gemm<128, 6, false>(tmap, p, grid, st);
+    case 64: return x3 ? launch_conv_gemm<64, 4, true>(tmap, p, grid, st) : launch_conv_gemm<64, 6, false>(tmap, p, grid, st);
+    case 32: return x3 ? launch_conv_gemm<32, 4, true>(tmap, p, grid, st) : launch_conv_gemm<32, 6, false>(tmap, p, grid, st);
+    case 16: return x3 ? launch_conv_gemm<16, 4, true>(tmap, p, grid, st) : launch_conv_gemm<16, 6, false>(tmap, p, grid, st);
     default: return MDGAN_ERR_UNSUPPORTED;
   }
 }

@@ -135,6 +135,12 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// x rounded to the nearest TF32 (ties away from zero, like cvt.rna.tf32.f32) with two full-rate integer ops: the cvt
+// instruction runs on the slow conversion path (a K step of a 128-row tile needs 4096-12288 of them).
+__device__ __forceinline__ float tf32_round_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
 // ----------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4

@@ -28,12 +28,14 @@ struct WgradParams {
   int P;            // n_img*Hl*Wl
   int splits, pix_per_split;
   int lbo_a, sbo_a, lbo_b, sbo_b;  // descriptor byte offsets (see file header)
+  unsigned long long magic_hw, magic_w;  // ceil(2^40 / (Hl*Wl)), ceil(2^40 / Wl): q = (n * magic) >> 40 (exact, n < 2^28)
 };
 
 constexpr int kWM = 128;
 constexpr int kWK = 32;  // pixels per stage
 constexpr int kWProducerWarps = 8;
 constexpr int kWThreads = (kWProducerWarps + 1) * 32;
+constexpr int kWPrefetch = 3;  // K steps of operand loads kept in flight in registers per producer thread
 
 // Byte offset of 16-byte chunk `c16` (0..7) of pixel row `r` inside its 128-byte row under SWIZZLE_128B_BASE32B:
 // the 32-byte chunk index is XORed with (row & 3).
@@ -50,31 +52,29 @@ struct WgradSmem {
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;
-  // tf32x3: several TMEM accumulators to keep the truncating in-tensor-core accumulation chains short
-  // (see conv_gemm.cu); kMain round-robin accumulators for hi*hi plus one for the correction products.
-  static constexpr int kAccs = X3 ? (512 / BN > 16 ? 16 : 512 / BN) : 1;
-  static constexpr int kMain = X3 ? kAccs - 1 : 1;
-  static constexpr uint32_t kTmemCols = X3 ? kAccs * BN : BN;
+  // tf32x3: several TMEM accumulators keep the truncating in-tensor-core accumulation chains short (see
+  // conv_gemm.cu): K-slice k of a stage -> main accumulator k % kMain, plus one for the correction products.
+  static constexpr int kMain = X3 ? (BN > 64 ? 2 : 4) : 1;
+  static constexpr int kAccs = X3 ? kMain + 1 : 1;
+  static constexpr uint32_t kTmemCols = kAccs * BN <= 64 ? 64 : kAccs * BN <= 128 ? 128 : kAccs * BN <= 256 ? 256 : 512;
+  static_assert(kAccs * BN <= 512, "TMEM holds 512 columns");
 };
 
-// tf32x3 split of one 16-byte chunk in place (see conv_gemm.cu): hi stays, the remainder goes to +lo_delta.
-__device__ __forceinline__ void wsplit_chunk_x3(uint32_t hi_addr, uint32_t lo_delta) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi_addr));
-  // hi = x rounded to nearest TF32 (so the tensor core's truncation of hi is exact and the split is unbiased);
-  // lo = (x - hi) rounded to nearest TF32.  |lo| <= 2^-11 |x|, and the dropped lo*lo term is ~2^-22 relative.
-  float4 h, l;
-  h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-  l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr + lo_delta), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
-               : "memory");
+__device__ __forceinline__ void wsts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// store one 16-byte chunk rounded to TF32 (hi) and, for tf32x3, its exact remainder (lo) lo_delta bytes further
+template <bool X3>
+__device__ __forceinline__ void store_split(uint32_t addr, uint32_t lo_delta, const float4& v) {
+  const float hx = tf32_round_fast(v.x), hy = tf32_round_fast(v.y), hz = tf32_round_fast(v.z), hw = tf32_round_fast(v.w);
+  wsts128(addr, hx, hy, hz, hw);
+  if (X3) wsts128(addr + lo_delta, v.x - hx, v.y - hy, v.z - hz, v.w - hw);
 }
 
 template <int BN, int STAGES, bool X3>
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradParams p) {
   using S = WgradSmem<BN, STAGES, X3>;
-  constexpr int LAG = STAGES - 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
 
   if (warp < kWProducerWarps) {
     // ---------------------------------------------------------------- producers (both operands)
+    // global -> registers (kWPrefetch K steps ahead) -> TF32 hi/lo split in registers -> one swizzled store each.
     const uint32_t smem0 = smem_u32(smem);
     // A (Lo): 32 chunks of 16 B per pixel row (4 groups x 8 chunks); thread -> (cidx = tid%32, rows tid/32 + 8i)
     const int a_cidx = threadIdx.x & 31;
@@ -122,70 +123,66 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
     const int b_cidx = threadIdx.x % kBChunksPerRow;
     const int b_row0 = threadIdx.x / kBChunksPerRow;
     const int hw_l = p.Hl * p.Wl;
-    // tf32x3: every thread splits exactly the chunks it copied itself (visible to it after cp.async.wait_group)
-    auto split_stage = [&](int sd) {
-      const uint32_t a_stage = smem0 + sd * S::kStageBytes;
-      const uint32_t b_stage = a_stage + S::kABytes;
+    uint32_t a_soff[4], b_soff[kBPasses];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = a_row0 + 8 * i;
+      a_soff[i] = (a_cidx >> 3) * (kWK * 128) + r * 128 + swz32(a_cidx & 7, r);
+    }
+#pragma unroll
+    for (int i = 0; i < kBPasses; ++i) {
+      const int r = b_row0 + kBRowsPerPass * i;
+      b_soff[i] = S::kABytes + (b_cidx >> 3) * (kWK * 128) + r * 128 + swz32(b_cidx & 7, r);
+    }
+    int pbase_l = pix0;  // first pixel of the next K step to load
+    auto issue_loads = [&](float4(&abuf)[4], float4(&bbuf)[kBPasses]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int r = a_row0 + 8 * i;
-        wsplit_chunk_x3(a_stage + (a_cidx >> 3) * (kWK * 128) + r * 128 + swz32(a_cidx & 7, r), S::kHalfBytes);
+        const int pix = pbase_l + a_row0 + 8 * i;
+        abuf[i] = pix < pix1 ? __ldg(reinterpret_cast<const float4*>(p.lo + static_cast<size_t>(pix) * p.C1 + c1_0 + a_cidx * 4))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int i = 0; i < kBPasses; ++i) {
-        const int r = b_row0 + kBRowsPerPass * i;
-        wsplit_chunk_x3(b_stage + (b_cidx >> 3) * (kWK * 128) + r * 128 + swz32(b_cidx & 7, r), S::kHalfBytes);
-      }
-    };
-    for (int it = 0; it < ksteps; ++it) {
-      const int s = it % STAGES;
-      const uint32_t par = (it / STAGES) & 1;
-      mbar_wait(&empty_bar[s], par ^ 1);
-      const uint32_t a_stage = smem0 + s * S::kStageBytes;
-      const uint32_t b_stage = a_stage + S::kABytes;
-      const int pbase = pix0 + it * kWK;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = a_row0 + 8 * i;
-        const int pix = pbase + r;
-        const bool ok = pix < pix1;
-        const float* g = p.lo + (ok ? (static_cast<size_t>(pix) * p.C1 + c1_0 + a_cidx * 4) : 0);
-        const uint32_t d = a_stage + (a_cidx >> 3) * (kWK * 128) + r * 128 + swz32(a_cidx & 7, r);
-        cp_async_16(d, g, ok ? 16u : 0u);
-      }
-#pragma unroll
-      for (int i = 0; i < kBPasses; ++i) {
-        const int r = b_row0 + kBRowsPerPass * i;
-        const int pix = pbase + r;
+        const int pix = pbase_l + b_row0 + kBRowsPerPass * i;
         bool ok = pix < pix1;
         size_t off = 0;
         if (ok) {
-          const int img = pix / hw_l;
+          const int img = static_cast<int>((static_cast<unsigned long long>(pix) * p.magic_hw) >> 40);
           const int rem = pix - img * hw_l;
-          const int gi = rem / p.Wl, gj = rem - gi * p.Wl;
+          const int gi = static_cast<int>((static_cast<unsigned long long>(rem) * p.magic_w) >> 40);
+          const int gj = rem - gi * p.Wl;
           const int sh = gi * SI + dh, sw = gj * SI + dw;
           ok = sh >= 0 && sh < p.Hh && sw >= 0 && sw < p.Wh;
           off = (static_cast<size_t>((img * p.Hh + sh) * p.Wh + sw)) * p.C2 + c2_0 + b_cidx * 4;
         }
-        const float* g = p.hi + (ok ? off : 0);
-        const uint32_t d = b_stage + (b_cidx >> 3) * (kWK * 128) + r * 128 + swz32(b_cidx & 7, r);
-        cp_async_16(d, g, ok ? 16u : 0u);
+        bbuf[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.hi + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      cp_async_commit();
-      if (it >= LAG) {
-        cp_async_wait<LAG>();
-        const int sd = (it - LAG) % STAGES;
-        if (X3) split_stage(sd);
-        fence_proxy_async_smem();
-        mbar_arrive(&full_bar[sd]);
+      pbase_l += kWK;
+    };
+    float4 abuf[kWPrefetch][4], bbuf[kWPrefetch][kBPasses];
+#pragma unroll
+    for (int u = 0; u < kWPrefetch; ++u)
+      if (u < ksteps) issue_loads(abuf[u], bbuf[u]);
+    int s = 0;
+    uint32_t par = 0;
+    for (int it0 = 0; it0 < ksteps; it0 += kWPrefetch) {
+#pragma unroll
+      for (int u = 0; u < kWPrefetch; ++u) {
+        const int it = it0 + u;
+        if (it < ksteps) {
+          mbar_wait(&empty_bar[s], par ^ 1);
+          const uint32_t stage = smem0 + s * S::kStageBytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) store_split<X3>(stage + a_soff[i], S::kHalfBytes, abuf[u][i]);
+#pragma unroll
+          for (int i = 0; i < kBPasses; ++i) store_split<X3>(stage + b_soff[i], S::kHalfBytes, bbuf[u][i]);
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[s]);
+          if (it + kWPrefetch < ksteps) issue_loads(abuf[u], bbuf[u]);
+          if (++s == STAGES) { s = 0; par ^= 1; }
+        }
       }
-    }
-    cp_async_wait<0>();
-    for (int it = (ksteps > LAG ? ksteps - LAG : 0); it < ksteps; ++it) {
-      const int sd = it % STAGES;
-      if (X3) split_stage(sd);
-      fence_proxy_async_smem();
-      mbar_arrive(&full_bar[sd]);
     }
 
     // ---------------------------------------------------------------- epilogue: TMEM -> partial[split][tap]
@@ -205,16 +202,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
       if (ksteps > 0) {
         tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
         if (X3) {
-          const int valid = ksteps * (kWK / 8) < S::kMain ? ksteps * (kWK / 8) : S::kMain;
           float t[16];
-          for (int a = 1; a < valid; ++a) {
+#pragma unroll
+          for (int a = 1; a < S::kAccs; ++a) {
             tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col, t);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += t[j];
           }
-          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + S::kMain * BN + col, t);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += t[j];
         }
       } else {
 #pragma unroll
@@ -228,33 +222,33 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
     }
     tc_fence_before_sync();
   } else {
-    // ---------------------------------------------------------------- MMA issuer
+    // ---------------------------------------------------------------- MMA issuer (lean loop, see conv_gemm.cu)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(kWM, BN, 1, 1);
+      const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem), p.lbo_a, p.sbo_a, 1);
+      constexpr uint64_t kStageStep = S::kStageBytes >> 4, kBStep = S::kABytes >> 4, kLoStep = S::kHalfBytes >> 4;
+      int s = 0;
+      uint32_t par = 0;
+      uint64_t da0 = desc0;
       for (int it = 0; it < ksteps; ++it) {
-        const int s = it % STAGES;
-        const uint32_t par = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], par);
         tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
-        const uint32_t b_addr = a_addr + S::kABytes;
+        const uint32_t acc = it != 0 ? 1u : 0u;
 #pragma unroll
         for (int k = 0; k < kWK / 8; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * 1024, p.lbo_a, p.sbo_a, 1);
-          const uint64_t db = make_smem_desc_sw128(b_addr + k * 1024, p.lbo_b, p.sbo_b, 1);
+          const uint64_t da = da0 + 64 * k, db = da + kBStep;  // 8 pixels = two 512-byte k-atoms
           if (X3) {
-            const uint64_t da_lo = make_smem_desc_sw128(a_addr + S::kHalfBytes + k * 1024, p.lbo_a, p.sbo_a, 1);
-            const uint64_t db_lo = make_smem_desc_sw128(b_addr + S::kHalfBytes + k * 1024, p.lbo_b, p.sbo_b, 1);
-            const int g = it * (kWK / 8) + k;
             const uint32_t acc_corr = tmem_base + S::kMain * BN;
-            umma_tf32(acc_corr, da_lo, db, idesc, g != 0 ? 1u : 0u);
-            umma_tf32(acc_corr, da, db_lo, idesc, 1u);
-            umma_tf32(tmem_base + (g % S::kMain) * BN, da, db, idesc, g >= S::kMain ? 1u : 0u);
+            umma_tf32(acc_corr, da + kLoStep, db, idesc, k == 0 ? acc : 1u);
+            umma_tf32(acc_corr, da, db + kLoStep, idesc, 1u);
+            umma_tf32(tmem_base + (k % S::kMain) * BN, da, db, idesc, k < S::kMain ? acc : 1u);
           } else {
-            umma_tf32(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_base, da, db, idesc, k == 0 ? acc : 1u);
           }
         }
         umma_commit(&empty_bar[s]);
+        da0 += kStageStep;
+        if (++s == STAGES) { s = 0; par ^= 1; da0 = desc0; }
       }
       if (ksteps > 0) umma_commit(tmem_full_bar);
     }
@@ -269,6 +263,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
 template <int BN, int STAGES, bool X3>
 static int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
   using S = WgradSmem<BN, STAGES, X3>;
+  static_assert(S::kDynamic <= 227 * 1024, "shared memory per CTA");
   static bool configured = false;
   if (!configured) {
     MDGAN_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BN, STAGES, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -284,6 +279,9 @@ static int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
 // encoding, kept as a C-ABI knob for the parity tests.
 static int g_dbg_lbo = 0, g_dbg_sbo = 0;
 
+// Tile width of mdgan_wgrad_gemm for a given C2 (both precisions): 128 when it divides C2, else 64.
+static int wgrad_bn(int C2) { return C2 % 128 == 0 ? 128 : 64; }
+
 }  // namespace mdgan
 
 using namespace mdgan;
@@ -298,9 +296,9 @@ extern "C" void mdgan_debug_set_wgrad_desc(int lbo_bytes, int sbo_bytes) {
 extern "C" int mdgan_wgrad_splits(int n_img, int Hl, int Wl, int C1, int C2, int mode) {
   const int P = n_img * Hl * Wl;
   const int taps = mode == 0 ? 16 : 1;
-  const int bn = 64;  // conservative (the tf32x3 tile): never under-counts the slices either precision needs
+  const int bn = wgrad_bn(C2);
   const int tiles = (C1 / kWM) * (C2 / bn) * taps;
-  int splits = tiles >= 148 ? 1 : (148 + tiles - 1) / tiles;
+  int splits = tiles >= 148 ? 1 : 148 / tiles;  // one wave of CTAs: never spill a few tiles into a second wave
   const int max_splits = (P + 4 * kWK - 1) / (4 * kWK);  // at least 128 pixels per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -320,14 +318,16 @@ extern "C" int mdgan_wgrad_gemm(const float* lo, const float* hi, float* partial
   p.P = n_img * Hl * Wl;
   p.splits = splits;
   p.pix_per_split = ceil_div(ceil_div(p.P, splits), kWK) * kWK;
+  if (p.P >= (1 << 28) / (Hl * Wl > 0 ? 1 : 1) && static_cast<long long>(p.P) * Hl * Wl >= (1LL << 40)) return MDGAN_ERR_UNSUPPORTED;
+  p.magic_hw = ((1ULL << 40) + static_cast<unsigned long long>(Hl * Wl) - 1) / static_cast<unsigned long long>(Hl * Wl);
+  p.magic_w = ((1ULL << 40) + static_cast<unsigned long long>(Wl) - 1) / static_cast<unsigned long long>(Wl);
   p.lbo_a = p.lbo_b = g_dbg_lbo ? g_dbg_lbo : kWK * 128;  // distance between 32-channel groups
   p.sbo_a = p.sbo_b = g_dbg_sbo ? g_dbg_sbo : 512;        // distance between 4-pixel swizzle atoms
   const int taps = mode == 0 ? 16 : 1;
-  const int bn = (C2 % 128 == 0 && precision == 0) ? 128 : 64;  // tf32x3: BN = 64 leaves room for 7+1 accumulators
+  const int bn = wgrad_bn(C2);
   dim3 grid(C1 / kWM, C2 / bn, taps * splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision != 0 && precision != 1) return MDGAN_ERR_BAD_ARG;
-  if (precision == 1) return launch_wgrad<64, 4, true>(p, grid, st);
-  if (bn == 128) return launch_wgrad<128, 4, false>(p, grid, st);
-  return launch_wgrad<64, 4, false>(p, grid, st);
+  if (precision == 1) return bn == 128 ? launch_wgrad<128, 3, true>(p, grid, st) : launch_wgrad<64, 4, true>(p, grid, st);
+  return bn == 128 ? launch_wgrad<128, 6, false>(p, grid, st) : launch_wgrad<64, 6, false>(p, grid, st);
 }

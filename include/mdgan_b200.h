@@ -84,9 +84,6 @@ int mdgan_wgrad_unpack(const float* partial, float* grad, int mode, int splits, 
                        void* stream);
 int mdgan_reduce_slices(const float* partial, float* out, int slices, long long n, void* stream);
 void mdgan_debug_set_wgrad_desc(int lbo_bytes, int sbo_bytes);
-/* bottleneck probes for tools/conv_bench.py (1 skip hi/lo split, 2 skip gathers, 4 skip MMAs): results are INVALID
- * while a flag is set; 0 restores normal operation. */
-void mdgan_debug_set_conv_flags(int flags);
 
 /* ---- image-side ("thin", 1 or 3 channel) layers on CUDA cores -------------------------------------------------
  * mdgan_thin_down : img NCHW [n][CI][Hi][Wi], W [N][CI][4][4] -> out NHWC [n][Hi/2][Wi/2][N] (+ LeakyReLU).

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
     ("CIFAR10", 4, 8, 4, 1),             # BASELINE config 3 shape: N = 4, swap every epoch
     ("MNIST_DCGAN", 2, 16, 3, 10**6),    # BASELINE config 2 shape
     ("CelebA", 2, 8, 3, 1),
-    ("CelebA", 8, 4, 2, 1),              # BASELINE config 4 shape: N = 8 (k = 2)
+    ("CelebA", 8, 8, 2, 1),              # BASELINE config 4 shape: N = 8 (k = 2)
 ])
 def test_engine_matches_oracle(name, n_workers, b, epochs, swap):
     r = run_engine_vs_oracle(name, n_workers, b, epochs, swap, mode="trajectory")

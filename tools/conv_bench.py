@@ -10,7 +10,7 @@ from mdgan_b200 import _lib, ops
 dev = torch.device("cuda:0")
 prec = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dbg = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-_lib.load().mdgan_debug_set_conv_flags(dbg)
+pass  # debug probe flags were removed after the round-1 analysis
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
 def timeit(fn, reps=10):
@@ -30,6 +30,11 @@ layers = [("celebaD c2 down", 0, 128, 64, 128, 32), ("celebaD c3 down", 0, 128, 
           ("celebaG L2 up", 1, 128, 512, 256, 4), ("celebaG L3 up", 1, 128, 256, 128, 8), ("celebaG L4 up", 1, 128, 128, 64, 16),
           ("celebaG L5 up(nchw,3)", 1, 128, 64, 3, 32), ("mnistD c2 down", 0, 128, 64, 128, 14), ("mnistG L2 up", 1, 128, 256, 128, 7),
           ("b1024 celebaD c3", 0, 2048, 128, 256, 16)]
+only = os.environ.get('CONV_BENCH_ONLY')
+if only:
+    layers = [l for l in layers if only in l[0]]
+if os.environ.get('WGRAD_BENCH_ONLY'):
+    layers = []
 for label, mode, n, C, N, H in layers:
     x = torch.randn(n, H, H, C, device=dev)
     if mode == 0:
@@ -49,8 +54,9 @@ for label, mode, n, C, N, H in layers:
     us = timeit(fn)
     print(f"  {label:24s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s (algorithmic)")
 # wgrad
-for label, n, C1, C2, Hl in [("celebaD c3 wgrad", 128, 256, 128, 8), ("celebaD c4 wgrad", 128, 512, 256, 4), ("celebaG L3 wgrad", 128, 256, 128, 8),
-                             ("celebaD c2 wgrad", 128, 128, 64, 16), ("b1024 celebaD c3 wgrad", 2048, 256, 128, 8)]:
+wonly = os.environ.get('WGRAD_BENCH_ONLY')
+for label, n, C1, C2, Hl in [] if only else [w for w in [("celebaD c3 wgrad", 128, 256, 128, 8), ("celebaD c4 wgrad", 128, 512, 256, 4), ("celebaG L3 wgrad", 128, 256, 128, 8),
+                             ("celebaD c2 wgrad", 128, 128, 64, 16), ("b1024 celebaD c3 wgrad", 2048, 256, 128, 8)] if not wonly or wonly in w[0]]:
     lo = torch.randn(n, Hl, Hl, C1, device=dev); hi = torch.randn(n, 2 * Hl, 2 * Hl, C2, device=dev)
     splits = ops.wgrad_splits(n, Hl, Hl, C1, C2, ops.MODE_DOWN)
     partial = torch.empty(splits * 16 * C1 * C2, device=dev)

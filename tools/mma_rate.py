@@ -10,7 +10,7 @@ x = torch.randn(n, H, H, C, device=dev)
 W = torch.randn(N, C, 4, 4, device=dev) * 0.05
 out = torch.empty(n, H // 2, H // 2, N, device=dev)
 for dbg in (2, 0):
-    _lib.load().mdgan_debug_set_conv_flags(dbg)
+    pass  # debug probe flags were removed after the round-1 analysis
     for prec in (0, 1):
         wp = ops.pack_down(W, precision=prec)
         for bn in (32, 64, 128):
