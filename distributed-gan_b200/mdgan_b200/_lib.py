@@ -39,6 +39,7 @@ SIGNATURES = {
     "mdgan_pad_rows": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mdgan_sum_slices": (_i, [_p, _p, _ll, _i, _ll, _p]),
     "mdgan_thin_down": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "mdgan_thin_up": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_thin_wgrad_slices": (_i, [_i, _i, _i]),
     "mdgan_thin_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
 }

@@ -121,9 +121,116 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict
   for (int j = 0; j < KPT; ++j) o[j] = acc[j];
 }
 
+// thin_up: out[n, o, 2i+ph, 2j+pw] (NCHW, o < N in {1, 3}) = sum_{c, a, b} src[n, i+ph-a, j+pw-b, c] * W[c][o][kh][kw],
+// kh = (1-ph)+2a, kw = (1-pw)+2b: the 4-phase form of ConvTranspose2d(C -> N, k4, s2, p1) on an NHWC source, which is
+// also the data gradient of Conv2d(N -> C, k4, s2, p1) (W is then the conv weight [C][N][4][4]).  One thread per
+// low-resolution position computes its 2x2 output block for all N channels from the 3x3 source neighbourhood
+// (fp32 FMAs, weights broadcast from shared memory); optional tanh and accumulate-into-out epilogues.
+template <int N>
+__global__ void __launch_bounds__(128) thin_up_kernel(const float* __restrict__ src, const float* __restrict__ W,
+                                                      float* __restrict__ out, int n_img, int H, int Wd, int C,
+                                                      int act_tanh, int accumulate) {
+  extern __shared__ float w_s[];  // [C][N][16]
+  for (int i = threadIdx.x; i < C * N * 16; i += blockDim.x) w_s[i] = W[i];
+  __syncthreads();
+  const long long P = (long long)n_img * H * Wd;
+  const long long pix = blockIdx.x * 128LL + threadIdx.x;
+  if (pix >= P) return;
+  const int n = pix / (H * Wd);
+  const int rem = pix - (long long)n * H * Wd;
+  const int i = rem / Wd, j = rem - i * Wd;
+  float acc[2][2][N];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int o = 0; o < N; ++o) acc[a][b][o] = 0.f;
+  const float* base = src + ((long long)n * H * Wd) * C;
+  bool ok[3][3];
+  int off[3][3];
+#pragma unroll
+  for (int di = 0; di < 3; ++di)
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj) {
+      const int y = i + di - 1, x = j + dj - 1;
+      ok[di][dj] = y >= 0 && y < H && x >= 0 && x < Wd;
+      off[di][dj] = ok[di][dj] ? (y * Wd + x) * C : 0;
+    }
+  for (int c0 = 0; c0 < C; c0 += 4) {
+    float xs[3][3][4];
+#pragma unroll
+    for (int di = 0; di < 3; ++di)
+#pragma unroll
+      for (int dj = 0; dj < 3; ++dj) {
+        const float4 v = ok[di][dj] ? __ldg(reinterpret_cast<const float4*>(base + off[di][dj] + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xs[di][dj][0] = v.x; xs[di][dj][1] = v.y; xs[di][dj][2] = v.z; xs[di][dj][3] = v.w;
+      }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+      for (int o = 0; o < N; ++o) {
+        float w[16];
+        const float4* wp = reinterpret_cast<const float4*>(w_s + ((c0 + cc) * N + o) * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = wp[q];
+          w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+        }
+        // phase ph uses source rows di-1 in {ph-1, ph}: (ph=0: di=1 -> kh=1, di=0 -> kh=3; ph=1: di=2 -> kh=0, di=1 -> kh=2)
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+          for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                const int di = 1 + ph - a, dj = 1 + pw - b;
+                const int kh = (1 - ph) + 2 * a, kw = (1 - pw) + 2 * b;
+                acc[ph][pw][o] = fmaf(xs[di][dj][cc], w[kh * 4 + kw], acc[ph][pw][o]);
+              }
+      }
+    }
+  }
+  const int Ho = 2 * H, Wo = 2 * Wd;
+#pragma unroll
+  for (int o = 0; o < N; ++o)
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+      float2* dst = reinterpret_cast<float2*>(out + (((long long)n * N + o) * Ho + 2 * i + ph) * Wo + 2 * j);
+      float2 r = make_float2(acc[ph][0][o], acc[ph][1][o]);
+      if (act_tanh) { r.x = tanhf(r.x); r.y = tanhf(r.y); }
+      if (accumulate) { const float2 prev = *dst; r.x += prev.x; r.y += prev.y; }
+      *dst = r;
+    }
+}
+
 }  // namespace mdgan
 
 using namespace mdgan;
+
+extern "C" int mdgan_thin_up(const float* src, const float* W, float* out, int n_img, int H, int Wd, int C, int N,
+                             int act_tanh, int accumulate, void* stream) {
+  if (!src || !W || !out) return MDGAN_ERR_BAD_ARG;
+  if ((N != 1 && N != 3) || C % 4 != 0 || C <= 0 || C > 256) return MDGAN_ERR_UNSUPPORTED;
+  const long long P = (long long)n_img * H * Wd;
+  const unsigned blocks = (unsigned)((P + 127) / 128);
+  const size_t smem = (size_t)C * N * 16 * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 3) {
+    static bool configured = false;
+    if (!configured) {
+      MDGAN_CUDA(cudaFuncSetAttribute(thin_up_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 3 * 16 * 4));
+      configured = true;
+    }
+    thin_up_kernel<3><<<blocks, 128, smem, st>>>(src, W, out, n_img, H, Wd, C, act_tanh, accumulate);
+  } else {
+    thin_up_kernel<1><<<blocks, 128, smem, st>>>(src, W, out, n_img, H, Wd, C, act_tanh, accumulate);
+  }
+  MDGAN_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int mdgan_thin_down(const float* img, const float* W, float* out, int n_img, int CI, int Hi, int Wi, int N,
                                int act, float slope, int round_tf32, void* stream) {

@@ -150,8 +150,10 @@ class DiscNet:
             if ly.bn:
                 for G in range(1, max_groups + 1):
                     ws = max(ws, ops.bn_workspace_floats(G, batch_size * Ho * Ho, Cc))
-            # conv data-grad operand (UP): conv weight [co][ci] read as [C=co][N=ci]
-            self.wq.append(torch.empty(ops.packed_shape(ops.MODE_UP, ly.c_in, Cc, precision=self.prec), **f))
+            # conv data-grad operand (UP): conv weight [co][ci] read as [C=co][N=ci]; the image-side layer 0 runs on
+            # CUDA cores straight from the PyTorch-layout weight (ops.thin_up)
+            self.wq.append(torch.empty(ops.packed_shape(ops.MODE_UP, ly.c_in, Cc, precision=self.prec), **f)
+                           if l >= 1 else None)
             if l >= 1:
                 self.wp.append(torch.empty(ops.packed_shape(ops.MODE_DOWN, Cc, ly.c_in, precision=self.prec), **f))
                 splits = ops.wgrad_splits(nmax, Ho, Ho, Cc, ly.c_in, ops.MODE_DOWN)
@@ -176,8 +178,8 @@ class DiscNet:
     def repack(self) -> None:
         P = self.state.p
         for l, ly in enumerate(self.L[:-1]):
-            ops.pack_up(P[ly.weight], self.wq[l])
             if l >= 1:
+                ops.pack_up(P[ly.weight], self.wq[l])
                 ops.pack_down(P[ly.weight], self.wp[l])
         ops.head_pack(P[self.L[-1].weight], self.w_head)
 
@@ -237,9 +239,7 @@ class DiscNet:
         if train:
             ops.thin_wgrad(self.dz[0][:n], img[:n], self.partial[0], Gd[l0.weight])
         else:
-            ops.conv_gemm(self.dz[0][:n], self.wq[0], ops.MODE_UP, l0.c_in, self.feedback if out is None else out,
-                          (n, l0.h_out, l0.h_out), (l0.h_out, l0.h_out), out_nchw=True, accumulate=accumulate,
-                          precision=self.prec)
+            ops.thin_up(self.dz[0][:n], P[l0.weight], self.feedback if out is None else out, accumulate=accumulate)
 
     # ------------------------------------------------------------------ worker-level steps
     def train_step(self, real: torch.Tensor, x_d: torch.Tensor) -> torch.Tensor:
@@ -301,7 +301,8 @@ class GenNet:
         self.wp_dg.append(None)
         for l in range(1, len(L)):
             ly = L[l]
-            self.wq.append(torch.empty(ops.packed_shape(ops.MODE_UP, ly.c_out, ly.c_in, precision=self.prec), **f))
+            self.wq.append(torch.empty(ops.packed_shape(ops.MODE_UP, ly.c_out, ly.c_in, precision=self.prec), **f)
+                           if l < len(L) - 1 else None)   # the image-side last layer runs on CUDA cores (ops.thin_up)
             if l < len(L) - 1:
                 self.wp_dg.append(torch.empty(ops.packed_shape(ops.MODE_DOWN, ly.c_in, ly.c_out, precision=self.prec), **f))
                 sp = ops.wgrad_splits(n, ly.h_in, ly.h_in, ly.c_in, ly.c_out, ops.MODE_DOWN)
@@ -316,10 +317,9 @@ class GenNet:
     def repack(self) -> None:
         P, L = self.state.p, self.L
         ops.pack_dense(P[L[0].weight], self.wp_dense)
-        for l in range(1, len(L)):
+        for l in range(1, len(L) - 1):
             ops.pack_up(P[L[l].weight], self.wq[l])
-            if l < len(L) - 1:
-                ops.pack_down(P[L[l].weight], self.wp_dg[l])
+            ops.pack_down(P[L[l].weight], self.wp_dg[l])
 
     def adam(self) -> None:
         s = self.state
@@ -344,8 +344,7 @@ class GenNet:
                            1, n * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd, eps=bn.eps,
                            momentum=bn.momentum)
         last = L[-1]
-        ops.conv_gemm(self.a[-1], self.wq[-1], ops.MODE_UP, last.c_out, self.X, (n, last.h_in, last.h_in),
-                      (last.h_in, last.h_in), out_nchw=True, act_tanh=True, precision=self.prec)
+        ops.thin_up(self.a[-1], P[last.weight], self.X, act_tanh=True)
         return self.X
 
     def backward(self, s: torch.Tensor, scale: float) -> None:

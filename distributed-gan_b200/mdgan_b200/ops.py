@@ -185,6 +185,17 @@ def thin_down(img: torch.Tensor, W: torch.Tensor, out: torch.Tensor, act: int = 
     return out
 
 
+def thin_up(src: torch.Tensor, W: torch.Tensor, out: torch.Tensor, act_tanh: bool = False,
+            accumulate: bool = False) -> torch.Tensor:
+    """src NHWC [n, H, W, C], W [C, N, 4, 4] (N in {1, 3}) -> out NCHW [n, N, 2H, 2W]; optional tanh / += ."""
+    n, H, Wd, Cc = src.shape
+    N = W.shape[1]
+    _run("thin_up", 1, 2.0 * n * H * Wd * 16 * Cc * N, 4.0 * (src.numel() + out.numel() * (2 if accumulate else 1)),
+         lambda: _lib.load().mdgan_thin_up(_ptr(src), _ptr(W), _ptr(out), n, H, Wd, Cc, N, int(act_tanh),
+                                           int(accumulate), _stream()))
+    return out
+
+
 def thin_wgrad_slices(n_img: int, Hl: int, Wl: int) -> int:
     return _lib.load().mdgan_thin_wgrad_slices(n_img, Hl, Wl)
 

@@ -90,9 +90,15 @@ void mdgan_debug_set_wgrad_desc(int lbo_bytes, int sbo_bytes);
  *   Replaces nn.Conv2d(3,64,4,2,1)+LeakyReLU CIFAR10.py:85-86 / CelebA.py:78,96 and the data gradient of the
  *   last ConvTranspose2d (CIFAR10.py:130, CelebA.py:131).
  * mdgan_thin_wgrad: feat NHWC [n][Hl][Wl][C1], img NCHW [n][CI][2Hl][2Wl] -> partial [slices][C1][CI*16];
- *   reduce with mdgan_reduce_slices.  Weight gradient of those two layers. */
+ *   reduce with mdgan_reduce_slices.  Weight gradient of those two layers.
+ * mdgan_thin_up   : src NHWC [n][H][W][C], W [C][N][4][4], N in {1,3} -> out NCHW [n][N][2H][2W] (+ tanh, or += ):
+ *   the last ConvTranspose2d of the generator with its tanh (CIFAR10.py:130-131, CelebA.py:131,140) and the data
+ *   gradient of the first discriminator conv, i.e. the error feedback written (accumulated) into its slot
+ *   (actors/worker.py:227-233).  fp32 FMAs on CUDA cores in both precision modes. */
 int mdgan_thin_down(const float* img, const float* W, float* out, int n_img, int CI, int Hi, int Wi, int N, int act,
                     float slope, int round_tf32, void* stream);
+int mdgan_thin_up(const float* src, const float* W, float* out, int n_img, int H, int Wd, int C, int N, int act_tanh,
+                  int accumulate, void* stream);
 int mdgan_thin_wgrad_slices(int n_img, int Hl, int Wl);
 int mdgan_thin_wgrad(const float* feat, const float* img, float* partial, int n_img, int CI, int Hl, int Wl, int C1,
                      void* stream);

@@ -218,7 +218,7 @@ class OracleMDGAN:
         X = self.G(z)  # server.py:220 (train-mode BN over all k*b samples)
         K = torch.chunk(X, k)  # server.py:223
         feedbacks = torch.zeros((N, b, *self.shape), dtype=self.dtype)
-        d_losses, g_losses, reals = [], [], []
+        d_losses, g_losses, reals, d_mid = [], [], [], []
         for n in range(N):
             ig, id_ = route(n, k)
             x_g, x_d = K[ig].detach(), K[id_].detach()
@@ -227,6 +227,8 @@ class OracleMDGAN:
                 losses = torch.zeros(self.local_epochs)
                 for l in range(self.local_epochs):  # worker.py:193-213
                     losses[l] = d_train_step(self.D[n], self.opt_d[n], real, x_d)
+                if record:  # discriminator state after its Adam step(s), before the feedback pass (test hook)
+                    d_mid.append({kk: v.detach().clone() for kk, v in self.D[n].state_dict().items()})
                 loss_gen, F_n = d_feedback(self.D[n], x_g)  # worker.py:220-233
             feedbacks[n] = F_n
             d_losses.append(losses.mean().item())
@@ -252,7 +254,7 @@ class OracleMDGAN:
                 self.D[c - 1].load_state_dict(sa)
         out.update(mean_d_loss=d_losses, loss_gen=g_losses, pairs=pairs)
         if record:
-            out.update(z=z, X=X.detach(), feedbacks=feedbacks, delta_w=[g.detach() for g in delta_w], real=reals)
+            out.update(z=z, X=X.detach(), feedbacks=feedbacks, delta_w=[g.detach() for g in delta_w], real=reals, d_mid=d_mid)
         return out
 
 

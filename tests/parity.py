@@ -11,8 +11,11 @@ iterations (tools/drift_calibration.py; numbers in DESIGN.md).  Parity is theref
       and step counts, taken from the fp32 oracle), runs ONE full iteration in the engine, and must reproduce
       the oracle's generated batch, per-worker losses, group-summed feedback, Adam moments and post-step weights
       within TOL -- against the fp32 oracle, or, where a rounding-tied gate makes the fp32 oracle itself deviate
-      from exact arithmetic, against the fp64 twin started from the same state (`agrees`, tests/util.py).  Swap
-      pairs, routing and num_batches_tracked are bit-exact.
+      from exact arithmetic, against the fp64 twin started from the same state (`agrees`, tests/util.py).  The
+      reference state is also re-imposed at the two points inside an iteration where a sign-like Adam step would
+      turn one tied gate into an O(1e-1) downstream difference (after the discriminators' Adam step, before the
+      generator backward), so that every phase is judged on its own arithmetic.  Swap pairs, routing and
+      num_batches_tracked are bit-exact.
   free-running     : the engine carries its own state for E iterations; its drift from the fp32 oracle must stay
       within FREE_TOL (a bound of the same order as the fp32-vs-fp64 drift of the reference itself).
 """
@@ -30,8 +33,7 @@ from util import agrees, plugin, relerr
 TOL = {
     "loss": 2e-4,      # relative, per-worker mean_d_loss and loss_gen
     "X": 1e-3,         # generated batch
-    "S": 1e-3,         # group-summed feedback = grad-output of the generator backward, per image (REPORTED: the
-                       # asserted bound is the calibrated rel. L2 below)
+    "S": 1e-3,         # group-summed feedback = grad-output of the generator backward, per image
     "moments": 5e-3,   # Adam exp_avg after the step (== gradient parity), rel. L2 over the flat buffer (one tied
                        # gate in the training pass moves it by ~1e-3; gate-free runs measure ~1e-6..3e-5)
     "update": 1e-1,    # rel. L2 of the applied weight update (w_after - w_before).  Adam's first steps are sign-like
@@ -41,15 +43,11 @@ TOL = {
     "abs_w": 2.1,      # max |w_ours - w_ref| in units of lr
     "running": 1e-3,   # BatchNorm running statistics
 }
-# Feedback bound (rel. L2 of the whole group-summed tensor): S_L2_FLOOR, or S_TWIN_FACTOR x the deviation of the
-# reference's own fp64 twin from its fp32 run in the same iteration, whichever is larger.  Gate- and flip-free
-# iterations measure 5e-7..4e-5; one tied gate costs 5e-4..6e-3; and the feedback is computed AFTER the worker's Adam
-# step, whose first steps are sign-like: in the CelebA N=8 case the reference's fp32 and fp64 runs take a different
-# lr-step on ~250 of 2.77M weights per discriminator and their per-image feedbacks then differ by 3e-2..1.4e-1 for
-# every image of two of the eight workers (measured) -- no fp32 implementation can be closer to
-# the reference than the reference is to itself.
-S_L2_FLOOR = 1e-2
-S_TWIN_FACTOR = 3.0
+# Feedback (judged on the reference's post-Adam discriminator weights, see run_engine_vs_oracle): a rounding-tied gate
+# in the feedback pass corrupts one image (BatchNorm spreads a little of it over its batch), so at most S_BAD_IMAGES of
+# the k*b images may miss TOL["S"] while the whole tensor stays within S_L2 (rel. L2; clean iterations: 5e-7..4e-5).
+S_BAD_IMAGES = 0.25
+S_L2 = 1e-2
 # free-running drift bounds after <= 4 iterations (rel. L2)
 FREE_TOL = {"loss": 5e-2, "X": 5e-2, "weights_l2": 2e-2}
 
@@ -147,8 +145,9 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
     sources = {n: _DeviceBatches(routing.RealBatchStream(dataset, shards[n], batch_size), dev, mod.SHAPE)
                for n in range(n_workers)}
     engine = MDGANEngine(cfg, 0, 1, dev, g, discs, sources)
+    scratch = copy.deepcopy(discs[0])  # (constructing a new module would consume the global RNG stream)
     k, b = engine.k, batch_size
-    worst = {c: 0.0 for c in (list(TOL) + ["S_bad_images", "S_l2", "S_twin_l2"] if mode == "trajectory" else FREE_TOL)}
+    worst = {c: 0.0 for c in (list(TOL) + ["S_bad_images", "S_l2"] if mode == "trajectory" else FREE_TOL)}
     failures: List[str] = []
     pairs_ok, nbt_ok = True, True
 
@@ -165,7 +164,29 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
         ref = oracle.step(e, record=True)
         ref64 = twin.step(e, record=True, z=ref["z"], replay_reals=ref["real"], pairs=ref["pairs"]) if twin else None
         engine.generate()
-        engine.train_workers()
+        w_after_adam = {}
+        if mode == "trajectory":
+            # engine.train_workers(), with the reference's post-Adam discriminator state loaded between the training
+            # step and the feedback pass: the first Adam steps are sign-like, so ONE rounding-tied gate in the
+            # training pass (gradient off by ~5e-4 rel. L2) flips ~1e-4 of the lr-steps and moves the feedback of
+            # that worker by ~6e-2 -- the feedback kernels are judged on the reference's weights, the Adam step on
+            # the "moments"/"update"/"abs_w" metrics below.
+            engine.S.zero_()
+            for i, n in enumerate(engine.local):
+                ig, id_ = routing.route(n, k)
+                x_g, x_d = engine.X[ig * b:(ig + 1) * b], engine.X[id_ * b:(id_ + 1) * b]
+                real = engine.real_sources[n]()
+                net = engine.disc[n]
+                for l in range(local_epochs):
+                    engine.d_loss[i, l].copy_(net.train_step(real, x_d))
+                w_after_adam[n] = net.state.params.detach().double().cpu().clone()
+                scratch.load_state_dict(ref["d_mid"][n])
+                net.state.load_from(scratch)
+                net.repack()
+                slot = routing.feedback_slot(n, k)
+                engine.g_loss[i].copy_(net.feedback_step(x_g, out=engine.S[slot * b:(slot + 1) * b], accumulate=True))
+        else:
+            engine.train_workers()
         S_ref = torch.zeros((k, b, *mod.SHAPE))
         S_ref64 = torch.zeros((k, b, *mod.SHAPE), dtype=torch.float64)
         for n in range(n_workers):
@@ -184,16 +205,16 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
         if (pairs is None) != (ref["pairs"] is None) or (pairs is not None and not torch.equal(pairs, ref["pairs"])):
             pairs_ok = False
         if trace:
-            print(f"  iter {e}: X {relerr(engine.X, ref['X']):.2e} S {relerr(S, S_ref):.2e} loss {loss_err:.2e}", flush=True)
+            print(f"  iter {e}: X {relerr(engine.X, ref['X']):.2e} S {relerr(S, S_ref):.2e} loss {loss_err:.2e}\n"
+                  f"     d_loss {d_l} ref {ref['mean_d_loss']}\n     g_loss {g_l} ref {ref['loss_gen']}\n"
+                  f"     per-slot S err {[relerr(S[i], S_ref[i]) for i in range(k)]}", flush=True)
         if mode == "trajectory":
             check("loss", f"loss@{e}", loss_err <= TOL["loss"], loss_err)
             check("X", f"X@{e}", agrees(engine.X, ref["X"], ref64["X"], TOL["X"]), relerr(engine.X, ref["X"]))
             bad_frac, s_err, s_l2 = feedback_parity(S, S_ref, S_ref64)
-            twin_l2 = l2err(S_ref64, S_ref)
-            worst["S"] = max(worst["S"], s_err if bad_frac < 1.0 else 1.0)          # reported: images within TOL["S"]
-            worst["S_bad_images"] = max(worst["S_bad_images"], bad_frac)             # reported
-            worst["S_twin_l2"] = max(worst["S_twin_l2"], twin_l2)                     # reported
-            check("S_l2", f"S_l2@{e}", s_l2 <= max(S_L2_FLOOR, S_TWIN_FACTOR * twin_l2), s_l2)
+            check("S", f"S@{e}", s_err <= TOL["S"], s_err)
+            check("S_bad_images", f"S_bad_images@{e}", bad_frac <= S_BAD_IMAGES, bad_frac)
+            check("S_l2", f"S_l2@{e}", s_l2 <= S_L2, s_l2)
             engine.sync_modules()
             # after a swap worker a holds what partner c trained: compare module-for-module (oracle swapped too)
             nets = [("G", engine.gen, g, oracle.G, oracle.opt_g, twin.G, twin.opt_g)]
@@ -205,9 +226,17 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
                 m_ref, m_ref64 = _adam_flat(opt, theirs, "exp_avg"), _adam_flat(opt64, theirs64, "exp_avg")
                 m_err = min(l2err(net.state.m, m_ref), l2err(net.state.m, m_ref64))
                 check("moments", f"m[{label}]@{e}", m_err <= TOL["moments"], m_err)
-                src = label if label == "G" or not part else part[label + 1] - 1  # whose pre-step weights these were
-                wb = w_before[src]
-                wa_ref, wa_ref64, wa = _flat(theirs.parameters()), _flat(theirs64.parameters()), _flat(ours.parameters())
+                if trace:
+                    print(f"     moments[{label}]@{e} {m_err:.2e}", flush=True)
+                if label == "G":
+                    wb = w_before["G"]
+                    wa_ref, wa_ref64, wa = _flat(theirs.parameters()), _flat(theirs64.parameters()), _flat(ours.parameters())
+                else:  # the Adam step of worker `label`, before the reference state was loaded / any swap
+                    wb = w_before[label]
+                    names = [kk for kk, _ in theirs.named_parameters()]
+                    wa_ref = torch.cat([ref["d_mid"][label][kk].reshape(-1).double() for kk in names])
+                    wa_ref64 = torch.cat([ref64["d_mid"][label][kk].reshape(-1).double() for kk in names])
+                    wa = w_after_adam[label]
                 u_err = min(l2err(wa - wb, wa_ref - wb), l2err(wa - wb, wa_ref64 - wb))
                 check("update", f"update[{label}]@{e}", u_err <= TOL["update"], u_err)
                 a_err = (wa - wa_ref).abs().max().item() / lr

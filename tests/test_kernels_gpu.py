@@ -153,6 +153,30 @@ def test_thin_down_and_wgrad(ops, dev, CI, N, H):
     assert relerr(grad, Wd.grad) < FP32_TOL
 
 
+@pytest.mark.parametrize("n,C,N,H", [(4, 64, 3, 32), (4, 128, 3, 16), (5, 128, 1, 14), (3, 64, 1, 14), (64, 64, 3, 16)])
+def test_thin_up(ops, dev, n, C, N, H):
+    """ConvTranspose2d(C -> N, 4, 2, 1) (+ tanh) / the data gradient of Conv2d(N -> C, 4, 2, 1), NCHW output, += mode."""
+    torch.manual_seed(13)
+    x, W = torch.randn(n, C, H, H), torch.randn(C, N, 4, 4) * 0.05
+    ref = F.conv_transpose2d(x.double(), W.double(), stride=2, padding=1)
+    out = torch.empty(n, N, 2 * H, 2 * H, device=dev)
+    ops.thin_up(nhwc(x).to(dev), W.to(dev), out)
+    assert relerr(out, ref) < FP32_TOL
+    ops.thin_up(nhwc(x).to(dev), W.to(dev), out, act_tanh=True)
+    assert relerr(out, torch.tanh(ref)) < FP32_TOL
+    base = torch.randn(n, N, 2 * H, 2 * H)
+    out = base.clone().to(dev)
+    for _ in range(2):
+        ops.thin_up(nhwc(x).to(dev), W.to(dev), out, accumulate=True)
+    assert relerr(out, base.double() + 2 * ref) < FP32_TOL
+    # the same call as the data gradient of the first discriminator conv
+    xin = torch.randn(n, N, 2 * H, 2 * H, dtype=torch.double, requires_grad=True)
+    Wc = torch.randn(C, N, 4, 4) * 0.05
+    F.conv2d(xin, Wc.double(), stride=2, padding=1).backward(x.double())
+    ops.thin_up(nhwc(x).to(dev), Wc.to(dev), out)
+    assert relerr(out, xin.grad) < FP32_TOL
+
+
 @pytest.mark.parametrize("G,b,H,C,act,slope", [(2, 8, 8, 128, 2, 0.2), (1, 16, 4, 512, 1, 0.0), (1, 4, 16, 64, 1, 0.0)])
 def test_batchnorm_fwd_bwd(ops, dev, G, b, H, C, act, slope):
     torch.manual_seed(8)
