@@ -152,6 +152,15 @@ class LaunchCounter:
         yield
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     path = REPO / "MEASURED_PEAKS.json"
     if path.exists():
@@ -224,7 +233,7 @@ def run_reference(args) -> None:
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(args, n_workers: int) -> dict:
@@ -380,6 +389,7 @@ def run_ours(args) -> None:
     roofline["avg_launch_us"] = a["ms"] * 1e3 / max(a["calls"], 1)
     roofline["launches_timed"] = a["calls"]
     roofline["share_of_step"] = a["ms"] / total_ms
+    engine.close()
     shares = {n: {"share": round(v["ms"] / total_ms, 4), "us_per_iter": round(v["ms"] * 1e3 / 4, 2),
                   "calls_per_iter": v["calls"] // 4} for n, v in sorted(per_op.items(), key=lambda t: -t[1]["ms"])}
     del engine
@@ -411,6 +421,7 @@ def run_ours(args) -> None:
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(local),
            "api": "MDGANEngine.iteration (the loop body of actors.server.start / actors.worker.start): host torch RNG "
                   "noise + host DataLoader batches -> pinned -> device, losses read back every iteration"}
+    engine.close()
     del engine
 
     if world > 1:
@@ -435,13 +446,19 @@ def run_ours(args) -> None:
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step, "per_op": shares,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main() -> None:
     args = parse_args()
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, torch warnings) are sent to stderr; the JSON goes to the saved descriptor.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
