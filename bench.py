@@ -301,7 +301,7 @@ def run_ours(args) -> None:
         gen = build_generator(mod, SEED) if rank == 0 else None
         cfg = EngineConfig(n_workers=n_workers, batch_size=b, z_dim=mod.Z_DIM, image_shape=shape, generator_lr=LR,
                            discriminator_lr=LR, beta_1=BETA_1, beta_2=BETA_2, swap_interval=10 ** 9, local_epochs=1,
-                           z_source=z_source)
+                           z_source=z_source, prefetch_host=not resident)
         if resident:
             src = {n: DeviceResidentBatches(routing.RealBatchStream(dataset, shards[n], b), dev, shape, 16) for n in local}
         else:
@@ -408,7 +408,7 @@ def run_ours(args) -> None:
     for i in range(args.steps):
         flush.zero_()
         ev2[i][0].record()
-        engine.iteration(i)                       # host RNG + pinned staging, H2D, the step
+        engine.iteration(i)                       # host RNG + pinned staging, H2D, the step (+ next step's host staging)
         loss_host[:, 0].copy_(engine.d_loss[:, 0], non_blocking=True)   # D2H of the step's result
         loss_host[:, 1].copy_(engine.g_loss, non_blocking=True)
         ev2[i][1].record()

@@ -11,6 +11,8 @@ from __future__ import annotations
 from pathlib import Path
 from typing import Dict, Optional, Tuple
 
+import os
+
 import torch
 import torch.utils.data
 
@@ -65,7 +67,7 @@ def start(
                        generator_lr=generator_lr,
                        discriminator_lr=generator_lr if discriminator_lr is None else discriminator_lr,
                        beta_1=beta_1, beta_2=beta_2, swap_interval=swap_interval, local_epochs=local_epochs,
-                       z_source=z_source)
+                       z_source=z_source, prefetch_host=os.environ.get("MDGAN_PREFETCH", "1") == "1")
     return run_node(backend=backend, proc=0, n_procs=n_procs, world_size=world_size, device=torch.device(device),
                     cfg=cfg, generator=generator, discriminators={r - 1: m for r, m in colocated_workers.items()},
                     dataset=dataset, epochs=epochs, log_interval=log_interval, log_folder=Path(log_folder),

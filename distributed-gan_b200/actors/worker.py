@@ -9,6 +9,8 @@ from __future__ import annotations
 from pathlib import Path
 from typing import Dict, Optional, Tuple
 
+import os
+
 import torch
 
 from datasets.DataPartitioner import DataPartitioner
@@ -57,7 +59,8 @@ def start(
         raise RuntimeError(f"GPU process {proc} hosts worker ranks {[n + 1 for n in hosted]}, got {sorted(r + 1 for r in discs)}")
     cfg = EngineConfig(n_workers=N, batch_size=batch_size, z_dim=z_dim, image_shape=tuple(image_shape),
                        generator_lr=generator_lr, discriminator_lr=discriminator_lr, beta_1=beta_1, beta_2=beta_2,
-                       swap_interval=swap_interval, local_epochs=local_epochs)
+                       swap_interval=swap_interval, local_epochs=local_epochs,
+                       prefetch_host=os.environ.get("MDGAN_PREFETCH", "1") == "1")
     run_node(backend=backend, proc=proc, n_procs=n_procs, world_size=world_size, device=torch.device(device), cfg=cfg,
              generator=None, discriminators=discs, dataset=data_partitioner.train_dataset, epochs=epochs,
              log_interval=log_interval, log_folder=Path(log_folder), dataset_name=dataset_name, iid=iid)

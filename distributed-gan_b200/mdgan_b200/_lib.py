@@ -26,6 +26,8 @@ SIGNATURES = {
     "mdgan_debug_set_wgrad_desc": (None, [_i, _i]),
     "mdgan_pack_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_wgrad_unpack": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mdgan_pack_job_words": (_i, []),
+    "mdgan_pack_weights_multi": (_i, [_p, _i, _i, _p]),
     "mdgan_reduce_slices": (_i, [_p, _p, _i, _ll, _p]),
     "mdgan_bn_workspace_floats": (_ll, [_i, _i, _i]),
     "mdgan_bn_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _f, _i, _p]),
@@ -33,7 +35,7 @@ SIGNATURES = {
     "mdgan_act_backward": (_i, [_p, _p, _p, _ll, _i, _f, _i, _p]),
     "mdgan_tanh_backward": (_i, [_p, _p, _p, _ll, _f, _p]),
     "mdgan_head_pack": (_i, [_p, _p, _i, _i, _p]),
-    "mdgan_head_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "mdgan_head_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "mdgan_head_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "mdgan_adam_step": (_i, [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _p]),
     "mdgan_pad_rows": (_i, [_p, _p, _i, _i, _i, _i, _p]),

@@ -2,6 +2,7 @@
 // the library does not link libcuda) with a small cache, plus library-level C-ABI utilities.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -52,6 +53,14 @@ int get_tmap_2d_f32(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_
   cache[key] = m;
   *out = m;
   return 0;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MDGAN_PDL");  // opt-in: measured on B200 (round 1) it does not shorten the captured step
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 }  // namespace mdgan

@@ -103,6 +103,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
   const int cchunks = p.C / kBK;
   const int ksteps = taps * cchunks;
 
+  pdl_trigger();  // the next kernel's CTAs may take SMs as they drain; it waits for this grid before touching memory
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], kNumProducerWarps * 32 + 1);
@@ -117,6 +118,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // barriers, TMEM and the descriptor prefetch overlapped the previous kernel's tail; its outputs are read below
 
   if (warp < kNumProducerWarps) {
     // ------------------------------------------------------------------ A producers
@@ -321,8 +323,7 @@ static int launch_conv_gemm(const CUtensorMap& tmap, const ConvGemmParams& p, di
                                     S::kDynamic));
     configured = true;
   }
-  conv_gemm_kernel<BN, STAGES, X3><<<grid, kThreads, S::kDynamic, st>>>(tmap, p);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH((conv_gemm_kernel<BN, STAGES, X3>), grid, dim3(kThreads), S::kDynamic, st, tmap, p);
   return 0;
 }
 

@@ -22,6 +22,7 @@ __device__ __forceinline__ float to_tf32(float x) {
 // split = 1 (tf32x3): out holds two matrices back to back, hi = tf32(w) and lo = tf32(w - hi).
 __global__ void pack_weights_kernel(const float* __restrict__ W, float* __restrict__ out, int mode, int N, int C,
                                     int N_pad, int C_pad, int KK, long long total, int split) {
+  pdl_enter();
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
   float v = 0.f;
@@ -50,11 +51,59 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, float* __restri
   if (split) out[total + idx] = to_tf32(v - hi);
 }
 
+// All weight re-packs of one network in ONE launch (after its Adam step).  jobs: n_jobs records of kPackJobWords
+// int64 words in device memory: {W ptr, out ptr, mode, N, C, N_pad, C_pad, KK, total elements, first block, split}.
+// mode 0..2 as above; mode 3 is the discriminator head re-order wt[hw*C + c] = w[c*HW + hw] (N = HW, no TF32 rounding:
+// the head runs in fp32 on CUDA cores).
+constexpr int kPackJobWords = 11;
+__global__ void pack_weights_multi_kernel(const long long* __restrict__ jobs, int n_jobs) {
+  pdl_enter();
+  int j = 0;
+  while (j + 1 < n_jobs && (long long)blockIdx.x >= jobs[(j + 1) * kPackJobWords + 9]) ++j;
+  const long long* jb = jobs + j * kPackJobWords;
+  const float* __restrict__ W = reinterpret_cast<const float*>(jb[0]);
+  float* __restrict__ out = reinterpret_cast<float*>(jb[1]);
+  const int mode = (int)jb[2], N = (int)jb[3], C = (int)jb[4], N_pad = (int)jb[5], C_pad = (int)jb[6], KK = (int)jb[7];
+  const long long total = jb[8];
+  const int split = (int)jb[10];
+  const long long idx = ((long long)blockIdx.x - jb[9]) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  float v = 0.f;
+  if (mode == 0) {
+    const int c = idx % C_pad;
+    const int tap = (idx / C_pad) % 16;
+    const int n = idx / (16LL * C_pad);
+    if (n < N && c < C) v = W[((long long)n * C + c) * 16 + tap];
+  } else if (mode == 1) {
+    const int c = idx % C_pad;
+    const int t = (idx / C_pad) % 4;
+    const int n = (idx / (4LL * C_pad)) % N_pad;
+    const int ph = idx / (4LL * C_pad * N_pad);
+    const int kh = (1 - (ph >> 1)) + 2 * (t >> 1);
+    const int kw = (1 - (ph & 1)) + 2 * (t & 1);
+    if (n < N && c < C) v = W[((long long)c * N + n) * 16 + kh * 4 + kw];
+  } else if (mode == 2) {
+    const int c = idx % C_pad;
+    const long long row = idx / C_pad;
+    const int n = row % N;
+    const int kk = row / N;
+    if (c < C) v = W[((long long)c * N + n) * KK + kk];
+  } else {
+    const int hw = idx / C, c = idx - (long long)hw * C;
+    out[idx] = W[(long long)c * N + hw];
+    return;
+  }
+  const float hi = to_tf32(v);
+  out[idx] = hi;
+  if (split) out[total + idx] = to_tf32(v - hi);
+}
+
 // Reduce split-K partial slices and scatter to the PyTorch parameter layout.
 // mode 0: grad[c1][c2][tap] = sum_s partial[s][tap][c1][c2]      (C1p x C2 slices, c1 < C1)
 // mode 2: grad[c1][n][kk]   = sum_s partial[s][0][c1][kk*N + n]  (dense first generator layer; C2 = KK*N)
 __global__ void wgrad_unpack_kernel(const float* __restrict__ partial, float* __restrict__ grad, int mode, int splits,
                                     int taps, int C1, int C1p, int C2, int N, int KK, long long total) {
+  pdl_enter();
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
   long long src;
@@ -76,19 +125,34 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ partial, float* __
   grad[idx] = acc;
 }
 
-__global__ void reduce_slices_kernel(const float* __restrict__ partial, float* __restrict__ out, int slices,
-                                     long long n) {
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= n) return;
+// out[i] = sum_s partial[s][i].  Block = 32 outputs x 8 slice lanes (fixed summation order: lane-strided partial sums,
+// then lanes 0..7), so a few hundred slices of a small tensor are read with 8-way parallelism per output.
+__global__ void __launch_bounds__(256) reduce_slices_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                            int slices, long long n) {
+  __shared__ float red[8][32];
+  pdl_enter();
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const long long idx = blockIdx.x * 32LL + o;
   float acc = 0.f;
-  for (int s = 0; s < slices; ++s) acc += partial[s * n + idx];
-  out[idx] = acc;
+  if (idx < n) {
+#pragma unroll 4
+    for (int s = sl; s < slices; s += 8) acc += partial[s * n + idx];
+  }
+  red[sl][o] = acc;
+  __syncthreads();
+  if (sl == 0 && idx < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += red[l][o];
+    out[idx] = t;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------- BatchNorm (train)
 // x is [G*Pg, C] (G independent passes of Pg rows each, e.g. real || X_d).  Stage 1: per-chunk partial sums.
 __global__ void bn_partial_kernel(const float* __restrict__ x, float* __restrict__ partial, int Pg, int C,
                                   int chunks_per_group, int rows_per_chunk) {
+  pdl_enter();
   extern __shared__ float sm[];  // [row_lanes][2][C]
   const int quads = C >> 2;
   const int row_lanes = blockDim.x / quads;
@@ -120,53 +184,48 @@ __global__ void bn_partial_kernel(const float* __restrict__ x, float* __restrict
 
 // Stage 2: per group (in order) mean / biased var -> scale, shift; running stats with momentum 0.1 and unbiased
 // variance, num_batches_tracked += G.  stats layout: [G][4][C] = mean, invstd, scale, shift.
-// Block = 32 channels x 8 chunk-lanes: the chunk partials of a channel are summed by 8 threads in fp64 and combined
-// through shared memory (a single thread walking all ~300 chunks cost 40-60 us of pure latency per launch).
-constexpr int kFinLanes = 8;
-__global__ void __launch_bounds__(32 * kFinLanes)
+// One warp per channel: the lanes stride the chunk partials (independent loads), fp64 butterfly reduction.
+__global__ void __launch_bounds__(256)
 bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
                    float* __restrict__ stats, int G, int Pg, int C, int chunks_per_group, float eps, float momentum) {
-  __shared__ double red[2][kFinLanes][32];
-  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += G;
-  const bool ok = c < C;
-  float rm = 0.f, rv = 0.f;
-  if (ok && lane == 0) { rm = running_mean ? running_mean[c] : 0.f; rv = running_var ? running_var[c] : 0.f; }
+  if (c >= C) return;
+  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+  const float gm = gamma[c], bt = beta[c];
   for (int g = 0; g < G; ++g) {
     double s = 0.0, ss = 0.0;
-    if (ok) {
-      for (int ch = lane; ch < chunks_per_group; ch += kFinLanes) {
-        const float* pp = partial + ((long long)(g * chunks_per_group + ch)) * 2 * C;
-        s += pp[c];
-        ss += pp[C + c];
-      }
+    const float* pg = partial + (long long)g * chunks_per_group * 2 * C + c;
+#pragma unroll 4
+    for (int ch = lane; ch < chunks_per_group; ch += 32) {
+      s += pg[(long long)ch * 2 * C];
+      ss += pg[(long long)ch * 2 * C + C];
     }
-    red[0][lane][cl] = s;
-    red[1][lane][cl] = ss;
-    __syncthreads();
-    if (ok && lane == 0) {
-      s = 0.0; ss = 0.0;
 #pragma unroll
-      for (int l = 0; l < kFinLanes; ++l) { s += red[0][l][cl]; ss += red[1][l][cl]; }
-      const double mean = s / Pg;
-      double var = ss / Pg - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-      const float sc = gamma[c] * invstd;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const double mean = s / Pg;
+    double var = ss / Pg - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gm * invstd;
+    const float unbiased = (float)(var * ((double)Pg / (double)(Pg > 1 ? Pg - 1 : 1)));
+    rm = (1.f - momentum) * rm + momentum * (float)mean;
+    rv = (1.f - momentum) * rv + momentum * unbiased;
+    if (lane == 0) {
       float* st = stats + (long long)g * 4 * C;
       st[c] = (float)mean;
       st[C + c] = invstd;
       st[2 * C + c] = sc;
-      st[3 * C + c] = beta[c] - (float)mean * sc;
-      const float unbiased = (float)(var * ((double)Pg / (double)(Pg > 1 ? Pg - 1 : 1)));
-      rm = (1.f - momentum) * rm + momentum * (float)mean;
-      rv = (1.f - momentum) * rv + momentum * unbiased;
+      st[3 * C + c] = bt - (float)mean * sc;
     }
-    __syncthreads();
   }
-  if (ok && lane == 0) {
+  if (lane == 0) {
     if (running_mean) running_mean[c] = rm;
     if (running_var) running_var[c] = rv;
   }
@@ -187,6 +246,7 @@ __device__ __forceinline__ float act_grad(float y, int act, float slope) {
 // Stage 3: out = act(x*scale + shift)
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, float* __restrict__ out,
                                 int Pg, int C, long long total4, int act, float slope, int round_tf32) {
+  pdl_enter();
   long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i4 >= total4) return;
   const long long e = i4 * 4;
@@ -209,6 +269,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
 __global__ void bn_bwd_partial_kernel(const float* __restrict__ da, const float* __restrict__ x,
                                       const float* __restrict__ stats, float* __restrict__ partial, int Pg, int C,
                                       int chunks_per_group, int rows_per_chunk, int act, float slope) {
+  pdl_enter();
   extern __shared__ float sm[];
   const int quads = C >> 2;
   const int row_lanes = blockDim.x / quads;
@@ -251,39 +312,36 @@ __global__ void bn_bwd_partial_kernel(const float* __restrict__ da, const float*
 }
 
 // Backward stage 2: sums[g][2][C] (sum dy, sum dy*xhat); dgamma/dbeta = totals over all groups (optional).
-// Same 32-channel x 8-lane layout as bn_finalize_kernel.
-__global__ void __launch_bounds__(32 * kFinLanes)
+// One warp per channel, as bn_finalize_kernel.
+__global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums, float* __restrict__ dgamma,
                        float* __restrict__ dbeta, int G, int C, int chunks_per_group) {
-  __shared__ double red[2][kFinLanes][32];
-  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  const bool ok = c < C;
+  pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
   double tg = 0.0, tb = 0.0;
   for (int g = 0; g < G; ++g) {
     double s = 0.0, ss = 0.0;
-    if (ok) {
-      for (int ch = lane; ch < chunks_per_group; ch += kFinLanes) {
-        const float* pp = partial + ((long long)(g * chunks_per_group + ch)) * 2 * C;
-        s += pp[c];
-        ss += pp[C + c];
-      }
+    const float* pg = partial + (long long)g * chunks_per_group * 2 * C + c;
+#pragma unroll 4
+    for (int ch = lane; ch < chunks_per_group; ch += 32) {
+      s += pg[(long long)ch * 2 * C];
+      ss += pg[(long long)ch * 2 * C + C];
     }
-    red[0][lane][cl] = s;
-    red[1][lane][cl] = ss;
-    __syncthreads();
-    if (ok && lane == 0) {
-      s = 0.0; ss = 0.0;
 #pragma unroll
-      for (int l = 0; l < kFinLanes; ++l) { s += red[0][l][cl]; ss += red[1][l][cl]; }
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
       sums[(long long)g * 2 * C + c] = (float)s;
       sums[(long long)g * 2 * C + C + c] = (float)ss;
-      tb += s;
-      tg += ss;
     }
-    __syncthreads();
+    tb += s;
+    tg += ss;
   }
-  if (ok && lane == 0) {
+  if (lane == 0) {
     if (dgamma) dgamma[c] = (float)tg;
     if (dbeta) dbeta[c] = (float)tb;
   }
@@ -294,6 +352,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ da, const float* _
                                     const float* __restrict__ stats, const float* __restrict__ sums,
                                     float* __restrict__ dx, int Pg, int C, long long total4, int act, float slope,
                                     int round_tf32) {
+  pdl_enter();
   long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i4 >= total4) return;
   const long long e = i4 * 4;
@@ -322,6 +381,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ da, const float* _
 // dz = da * act'(a) for an activation with no BatchNorm in front (a = act(z); sign(a) == sign(z) for slope > 0).
 __global__ void act_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a, float* __restrict__ dz,
                                long long total4, int act, float slope, int round_tf32) {
+  pdl_enter();
   long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i4 >= total4) return;
   const float4 av = reinterpret_cast<const float4*>(a)[i4];
@@ -338,6 +398,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ da, const float* __rest
 // d(pre-tanh) = s * (1 - x^2) * scale   (generator output layer; s = group-summed feedback, x = tanh output)
 __global__ void tanh_bwd_kernel(const float* __restrict__ s, const float* __restrict__ x, float* __restrict__ out,
                                 long long n, float scale) {
+  pdl_enter();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float xv = x[i];
@@ -348,6 +409,7 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ s, const float* __rest
 // wt[hw*C + c] = w[c*HW + hw]: the head weight re-ordered once per optimiser step to the NHWC order of the activations
 // so that the per-sample dot products below read both operands with coalesced float4 loads.
 __global__ void head_pack_kernel(const float* __restrict__ w, float* __restrict__ wt, int HW, int C) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW * C) return;
   const int hw = i / C, c = i - hw * C;
@@ -359,9 +421,11 @@ __global__ void head_pack_kernel(const float* __restrict__ w, float* __restrict_
 // Labels: samples of group g (n / b) use label[g].  One 256-thread block per sample.
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const float* __restrict__ a, const float* __restrict__ wt, const float* __restrict__ label,
-                float* __restrict__ prob, float* __restrict__ loss_terms, float* __restrict__ dlogit, int n_total, int b,
-                int L) {
+                float* __restrict__ prob, float* __restrict__ loss_terms, float* __restrict__ dlogit,
+                float* __restrict__ loss, unsigned int* __restrict__ counter, int n_total, int b, int G, int L) {
   __shared__ float red[8];
+  __shared__ bool last;
+  pdl_enter();
   const int n = blockIdx.x;
   const float4* row = reinterpret_cast<const float4*>(a + (long long)n * L);
   const float4* w4 = reinterpret_cast<const float4*>(wt);
@@ -391,28 +455,32 @@ head_fwd_kernel(const float* __restrict__ a, const float* __restrict__ wt, const
     const float pq = (1.f - p) * p;
     // BCELoss backward: (p - y) / max(p(1-p), 1e-12) / b; sigmoid backward: * p(1-p)
     dlogit[n] = ((p - y) / fmaxf(pq, 1e-12f)) * (1.f / (float)b) * pq;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
   }
-}
-
-// loss[g] = mean over the b samples of group g; loss[G] = sum over groups (the reference's d_loss).
-__global__ void head_loss_kernel(const float* __restrict__ loss_terms, float* __restrict__ loss, int G, int b) {
-  __shared__ float red[32];
+  __syncthreads();
+  if (!last) return;
+  // The last block to finish reduces the per-sample terms in a fixed order: loss[g] = mean over the b samples of
+  // group g; loss[G] = sum over groups (the reference's d_loss).
+  __threadfence();
+  if (threadIdx.x == 0) *counter = 0;
   float total = 0.f;
   for (int g = 0; g < G; ++g) {
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < b; i += blockDim.x) acc += loss_terms[g * b + i];
+    float t = 0.f;
+    for (int i = threadIdx.x; i < b; i += 256) t += __ldcg(loss_terms + g * b + i);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
     __syncthreads();
     if (threadIdx.x == 0) {
-      float s = 0.f;
-      for (int wv = 0; wv < (blockDim.x >> 5); ++wv) s += red[wv];
-      s /= (float)b;
-      loss[g] = s;
-      total += s;
+      float sgl = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) sgl += red[wv];
+      sgl /= (float)b;
+      loss[g] = sgl;
+      total += sgl;
     }
-    __syncthreads();
   }
   if (threadIdx.x == 0) loss[G] = total;
 }
@@ -421,6 +489,7 @@ __global__ void head_loss_kernel(const float* __restrict__ loss_terms, float* __
 __global__ void head_bwd_kernel(const float* __restrict__ a, const float* __restrict__ wt,
                                 const float* __restrict__ dlogit, float* __restrict__ da, float* __restrict__ dw,
                                 int n_total, int HW, int C) {
+  pdl_enter();
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const int L = HW * C;
   if (l >= L) return;
@@ -436,37 +505,65 @@ __global__ void head_bwd_kernel(const float* __restrict__ a, const float* __rest
 }
 
 // ----------------------------------------------------------------------------------------------- Adam (torch.optim.Adam)
-// step_count lives on the device so the launch is CUDA-graph friendly; adam_tick_kernel increments it afterwards.
+// step_count[0] lives on the device so the launch is CUDA-graph friendly; step_count[1] is a block counter: the last
+// block to finish (every block has read the step by then) writes the incremented step and clears the counter.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, int* __restrict__ step_count, float lr, float beta1,
-                            float beta2, float eps) {
+                            float beta2, float eps, int vec4) {
   __shared__ float s_step_size, s_bc2_sqrt;
+  __shared__ int s_t;
+  pdl_enter();
   if (threadIdx.x == 0) {
-    const int t = *step_count + 1;
+    const int t = *reinterpret_cast<volatile int*>(step_count) + 1;
     const double bc1 = 1.0 - pow((double)beta1, (double)t);
     const double bc2 = 1.0 - pow((double)beta2, (double)t);
     s_step_size = (float)((double)lr / bc1);
     s_bc2_sqrt = (float)sqrt(bc2);
+    s_t = t;
   }
   __syncthreads();
   const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i];
-    float mi = m[i], vi = v[i];
+  auto update = [&](float gi, float& pi, float& mi, float& vi) {
     mi = mi + (gi - mi) * (1.f - beta1);            // exp_avg.lerp_(grad, 1 - beta1)
     vi = vi * beta2 + (1.f - beta2) * gi * gi;      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);
+    pi = pi - step_size * (mi / denom);
+  };
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  const long long n4 = vec4 ? (n >> 2) : 0;  // float4 body (all four buffers 16-byte aligned), scalar tail
+  for (long long i = tid; i < n4; i += nthr) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    update(g4.x, p4.x, m4.x, v4.x);
+    update(g4.y, p4.y, m4.y, v4.y);
+    update(g4.z, p4.z, m4.z, v4.z);
+    update(g4.w, p4.w, m4.w, v4.w);
+    reinterpret_cast<float4*>(p)[i] = p4;
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+  }
+  for (long long i = n4 * 4 + tid; i < n; i += nthr) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    update(g[i], pi, mi, vi);
+    p[i] = pi;
     m[i] = mi;
     v[i] = vi;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(step_count + 1);
+    if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
+      *cnt = 0;
+      step_count[0] = s_t;
+    }
+  }
 }
-__global__ void adam_tick_kernel(int* step_count) { *step_count += 1; }
 
 // ----------------------------------------------------------------------------------------------- misc
 // out[r][c] (cols_out >= cols_in, zero padded), optionally rounded to TF32: pads z [kb, 100] to [kb, 128].
 __global__ void pad_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols_in,
                                 int cols_out, int round_tf32) {
+  pdl_enter();
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= (long long)rows * cols_out) return;
   const int c = idx % cols_out;
@@ -478,6 +575,7 @@ __global__ void pad_rows_kernel(const float* __restrict__ in, float* __restrict_
 // out[i] = sum_k in_k[i] over `count` equally sized slices spaced `stride` floats apart (feedback group sum).
 __global__ void sum_slices_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, int count,
                                   long long stride) {
+  pdl_enter();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float acc = 0.f;
@@ -498,9 +596,16 @@ extern "C" int mdgan_pack_weights(const float* W, float* out, int mode, int N, i
   if (mode == 0) total = (long long)N_pad * 16 * C_pad;
   else if (mode == 1) total = 4LL * N_pad * 4 * C_pad;
   else total = (long long)KK * N * C_pad;
-  pack_weights_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(W, out, mode, N, C, N_pad, C_pad, KK,
-                                                                                total, split);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(pack_weights_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, W, out, mode, N, C,
+               N_pad, C_pad, KK, total, split);
+  return 0;
+}
+
+extern "C" int mdgan_pack_job_words(void) { return kPackJobWords; }
+
+extern "C" int mdgan_pack_weights_multi(const long long* jobs_dev, int n_jobs, int total_blocks, void* stream) {
+  if (!jobs_dev || n_jobs <= 0 || total_blocks <= 0) return MDGAN_ERR_BAD_ARG;
+  MDGAN_LAUNCH(pack_weights_multi_kernel, dim3(total_blocks), dim3(256), 0, (cudaStream_t)stream, jobs_dev, n_jobs);
   return 0;
 }
 
@@ -509,15 +614,14 @@ extern "C" int mdgan_wgrad_unpack(const float* partial, float* grad, int mode, i
   if (!partial || !grad || (mode != 0 && mode != 2)) return MDGAN_ERR_BAD_ARG;
   const int taps = mode == 0 ? 16 : 1;
   const long long total = mode == 0 ? (long long)C1 * C2 * 16 : (long long)C1 * N * KK;
-  wgrad_unpack_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(partial, grad, mode, splits, taps, C1,
-                                                                                C1p, C2, N, KK, total);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(wgrad_unpack_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, partial, grad, mode,
+               splits, taps, C1, C1p, C2, N, KK, total);
   return 0;
 }
 
 extern "C" int mdgan_reduce_slices(const float* partial, float* out, int slices, long long n, void* stream) {
-  reduce_slices_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(partial, out, slices, n);
-  MDGAN_CHECK_LAUNCH();
+  if (!partial || !out || slices <= 0) return MDGAN_ERR_BAD_ARG;
+  MDGAN_LAUNCH(reduce_slices_kernel, dim3(blocks_for(n, 32)), dim3(256), 0, (cudaStream_t)stream, partial, out, slices, n);
   return 0;
 }
 
@@ -546,14 +650,13 @@ extern "C" int mdgan_bn_forward(const float* x, float* out, const float* gamma, 
   int cpg, rpc;
   bn_chunks(Pg, G, &cpg, &rpc);
   const int row_lanes = 256 / (C / 4);
-  bn_partial_kernel<<<G * cpg, 256, row_lanes * 2 * C * sizeof(float), st>>>(x, workspace, Pg, C, cpg, rpc);
-  MDGAN_CHECK_LAUNCH();
-  bn_finalize_kernel<<<blocks_for(C, 32), 32 * kFinLanes, 0, st>>>(workspace, gamma, beta, running_mean, running_var,
-                                                         num_batches_tracked, stats, G, Pg, C, cpg, eps, momentum);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(bn_partial_kernel, dim3(G * cpg), dim3(256), row_lanes * 2 * C * sizeof(float), st, x, workspace, Pg, C,
+               cpg, rpc);
+  MDGAN_LAUNCH(bn_finalize_kernel, dim3(blocks_for(C, 8)), dim3(256), 0, st, workspace, gamma, beta, running_mean,
+               running_var, num_batches_tracked, stats, G, Pg, C, cpg, eps, momentum);
   const long long total4 = (long long)G * Pg * C / 4;
-  bn_apply_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x, stats, out, Pg, C, total4, act, slope, round_tf32);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(bn_apply_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, x, stats, out, Pg, C, total4, act, slope,
+               round_tf32);
   return 0;
 }
 
@@ -566,88 +669,77 @@ extern "C" int mdgan_bn_backward(const float* da, const float* x, const float* s
   int cpg, rpc;
   bn_chunks(Pg, G, &cpg, &rpc);
   const int row_lanes = 256 / (C / 4);
-  bn_bwd_partial_kernel<<<G * cpg, 256, row_lanes * 2 * C * sizeof(float), st>>>(da, x, stats, workspace, Pg, C, cpg,
-                                                                               rpc, act, slope);
-  MDGAN_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<blocks_for(C, 32), 32 * kFinLanes, 0, st>>>(workspace, sums, dgamma, dbeta, G, C, cpg);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(bn_bwd_partial_kernel, dim3(G * cpg), dim3(256), row_lanes * 2 * C * sizeof(float), st, da, x, stats,
+               workspace, Pg, C, cpg, rpc, act, slope);
+  MDGAN_LAUNCH(bn_bwd_finalize_kernel, dim3(blocks_for(C, 8)), dim3(256), 0, st, workspace, sums, dgamma, dbeta, G, C, cpg);
   const long long total4 = (long long)G * Pg * C / 4;
-  bn_bwd_apply_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(da, x, stats, sums, dx, Pg, C, total4, act, slope,
-                                                               round_tf32);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(bn_bwd_apply_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, da, x, stats, sums, dx, Pg, C, total4,
+               act, slope, round_tf32);
   return 0;
 }
 
 extern "C" int mdgan_act_backward(const float* da, const float* a, float* dz, long long n, int act, float slope,
                                   int round_tf32, void* stream) {
   if (!da || !a || !dz || n % 4 != 0) return MDGAN_ERR_BAD_ARG;
-  act_bwd_kernel<<<blocks_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(da, a, dz, n / 4, act, slope, round_tf32);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(act_bwd_kernel, dim3(blocks_for(n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, da, a, dz, n / 4, act,
+               slope, round_tf32);
   return 0;
 }
 
 extern "C" int mdgan_tanh_backward(const float* s, const float* x, float* out, long long n, float scale,
                                    void* stream) {
   if (!s || !x || !out) return MDGAN_ERR_BAD_ARG;
-  tanh_bwd_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s, x, out, n, scale);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(tanh_bwd_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, s, x, out, n, scale);
   return 0;
 }
 
 extern "C" int mdgan_head_pack(const float* w, float* wt, int HW, int C, void* stream) {
   if (!w || !wt || HW <= 0 || C <= 0) return MDGAN_ERR_BAD_ARG;
-  head_pack_kernel<<<blocks_for((long long)HW * C, 256), 256, 0, (cudaStream_t)stream>>>(w, wt, HW, C);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(head_pack_kernel, dim3(blocks_for((long long)HW * C, 256)), dim3(256), 0, (cudaStream_t)stream, w, wt, HW, C);
   return 0;
 }
 
 extern "C" int mdgan_head_forward(const float* a, const float* wt, const float* label, float* prob, float* loss_terms,
-                                  float* dlogit, float* loss, int G, int b, int HW, int C, void* stream) {
-  if (!a || !wt || !label || !prob || !loss_terms || !dlogit || !loss) return MDGAN_ERR_BAD_ARG;
+                                  float* dlogit, float* loss, unsigned int* counter, int G, int b, int HW, int C,
+                                  void* stream) {
+  if (!a || !wt || !label || !prob || !loss_terms || !dlogit || !loss || !counter) return MDGAN_ERR_BAD_ARG;
   if (C % 4 != 0) return MDGAN_ERR_UNSUPPORTED;
-  cudaStream_t st = (cudaStream_t)stream;
   const int n_total = G * b;
-  head_fwd_kernel<<<n_total, 256, 0, st>>>(a, wt, label, prob, loss_terms, dlogit, n_total, b, HW * C);
-  MDGAN_CHECK_LAUNCH();
-  head_loss_kernel<<<1, 256, 0, st>>>(loss_terms, loss, G, b);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(head_fwd_kernel, dim3(n_total), dim3(256), 0, (cudaStream_t)stream, a, wt, label, prob, loss_terms, dlogit,
+               loss, counter, n_total, b, G, HW * C);
   return 0;
 }
 
 extern "C" int mdgan_head_backward(const float* a, const float* wt, const float* dlogit, float* da, float* dw,
                                    int n_total, int HW, int C, void* stream) {
   if (!a || !wt || !dlogit || !da) return MDGAN_ERR_BAD_ARG;
-  head_bwd_kernel<<<blocks_for((long long)HW * C, 128), 128, 0, (cudaStream_t)stream>>>(a, wt, dlogit, da, dw, n_total,
-                                                                                       HW, C);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(head_bwd_kernel, dim3(blocks_for((long long)HW * C, 128)), dim3(128), 0, (cudaStream_t)stream, a, wt, dlogit,
+               da, dw, n_total, HW, C);
   return 0;
 }
 
 extern "C" int mdgan_adam_step(float* p, const float* g, float* m, float* v, long long n, int* step_count, float lr,
                                float beta1, float beta2, float eps, void* stream) {
   if (!p || !g || !m || !v || !step_count) return MDGAN_ERR_BAD_ARG;
-  cudaStream_t st = (cudaStream_t)stream;
-  unsigned blocks = blocks_for(n, 256);
+  const int vec4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  unsigned blocks = blocks_for(vec4 ? (n + 3) / 4 : n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, step_count, lr, beta1, beta2, eps);
-  MDGAN_CHECK_LAUNCH();
-  adam_tick_kernel<<<1, 1, 0, st>>>(step_count);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, step_count, lr, beta1, beta2,
+               eps, vec4);
   return 0;
 }
 
 extern "C" int mdgan_pad_rows(const float* in, float* out, int rows, int cols_in, int cols_out, int round_tf32,
                               void* stream) {
   if (!in || !out || cols_out < cols_in) return MDGAN_ERR_BAD_ARG;
-  pad_rows_kernel<<<blocks_for((long long)rows * cols_out, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols_in,
-                                                                                                cols_out, round_tf32);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(pad_rows_kernel, dim3(blocks_for((long long)rows * cols_out, 256)), dim3(256), 0, (cudaStream_t)stream, in,
+               out, rows, cols_in, cols_out, round_tf32);
   return 0;
 }
 
 extern "C" int mdgan_sum_slices(const float* in, float* out, long long n, int count, long long stride, void* stream) {
   if (!in || !out) return MDGAN_ERR_BAD_ARG;
-  sum_slices_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n, count, stride);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH(sum_slices_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, in, out, n, count, stride);
   return 0;
 }

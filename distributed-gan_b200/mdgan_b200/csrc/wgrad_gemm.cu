@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
   const int dw = (p.mode == 0) ? (tap & 3) - 1 : 0;
   const int SI = (p.mode == 0) ? 2 : 1;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], kWProducerWarps * 32);
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp < kWProducerWarps) {
     // ---------------------------------------------------------------- producers (both operands)
@@ -270,8 +272,7 @@ static int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
                                     S::kDynamic));
     configured = true;
   }
-  wgrad_gemm_kernel<BN, STAGES, X3><<<grid, kWThreads, S::kDynamic, st>>>(p);
-  MDGAN_CHECK_LAUNCH();
+  MDGAN_LAUNCH((wgrad_gemm_kernel<BN, STAGES, X3>), grid, dim3(kWThreads), S::kDynamic, st, p);
   return 0;
 }
 

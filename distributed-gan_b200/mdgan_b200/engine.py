@@ -44,6 +44,8 @@ class EngineConfig:
     swap_interval: int = 1
     local_epochs: int = 1
     z_source: str = "host"      # "host": torch CPU randn in the reference's RNG order (parity); "device": CUDA Philox
+    prefetch_host: bool = False  # stage the NEXT iteration's host inputs (noise draw, loader batch) while the GPU runs
+                                 # the current one; the host RNG order of the reference is kept (see prefetch_next)
 
 
 class CudaNetFactory:
@@ -104,6 +106,7 @@ class MDGANEngine:
         self.last_pairs: Optional[torch.Tensor] = None
         self.graph = None
         self._uploaded = None
+        self._staged = False
         self.iterations_done = 0
 
     # ------------------------------------------------------------------------------------------ phases
@@ -112,7 +115,10 @@ class MDGANEngine:
         mode (z_source == "host") the noise consumes process 0's global torch RNG exactly like the reference; real
         batches come from the host loaders in reference order (worker.py:162-167).  Fills the pinned staging buffers,
         after making sure the previous iteration's uploads have read them (the host may run iterations ahead of the
-        GPU: nothing else in the loop synchronises)."""
+        GPU: nothing else in the loop synchronises).  A no-op when prefetch_next already staged this iteration."""
+        if self._staged:
+            self._staged = False
+            return
         if self._uploaded is not None:
             self._uploaded.synchronize()
         kb = self.k * self.b
@@ -136,6 +142,17 @@ class MDGANEngine:
             if self._uploaded is None:
                 self._uploaded = torch.cuda.Event()
             self._uploaded.record()
+
+    def prefetch_next(self, epoch: int, last: bool = False) -> None:
+        """Host/GPU overlap: called right after `device_iteration` of iteration `epoch` was launched, stages iteration
+        epoch + 1's host inputs while the GPU works.  Skipped when a swap is due at `epoch`: the reference draws the
+        swap permutation (server.py:321) from process 0's global RNG BEFORE the next noise batch, and that order is
+        kept; skipped on the last iteration so that no extra draw is consumed."""
+        if not self.cfg.prefetch_host or last or routing.swap_due(epoch, self.cfg.swap_interval, self.N):
+            return
+        self._staged = False
+        self.stage_inputs()
+        self._staged = True
 
     def generate(self, staged: bool = False) -> None:
         """staged=False: also runs the host staging and the uploads (one call per phase, as the actors use it)."""
@@ -214,9 +231,10 @@ class MDGANEngine:
             torch.cuda.synchronize(self.device)
         self.graph = None
 
-    def iteration(self, epoch: int) -> None:
+    def iteration(self, epoch: int, last: bool = False) -> None:
         self.stage_inputs()
         self.device_iteration()
+        self.prefetch_next(epoch, last)
         self.maybe_swap(epoch)
         self.iterations_done += 1
 

@@ -55,7 +55,7 @@ class FlatState:
         self.grad = torch.zeros(self.n_params, device=device, dtype=torch.float32)
         self.m = torch.zeros_like(self.grad)
         self.v = torch.zeros_like(self.grad)
-        self.step = torch.zeros(1, device=device, dtype=torch.int32)
+        self.step = torch.zeros(2, device=device, dtype=torch.int32)   # (steps taken, adam block counter)
         self.p: Dict[str, torch.Tensor] = {}
         self.g: Dict[str, torch.Tensor] = {}
         self.b: Dict[str, torch.Tensor] = {}
@@ -103,7 +103,7 @@ class FlatState:
                 self.v[off: off + k].copy_(st["exp_avg_sq"].detach().reshape(-1).to(self.device, torch.float32))
                 step = int(st["step"])
             off += k
-        self.step.fill_(step)
+        self.step[0:1].fill_(step)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Host copy in the module's own `state_dict()` key order (what torch.save of the reference writes)."""
@@ -168,20 +168,27 @@ class DiscNet:
         self.loss_terms = torch.zeros(nmax, **f)
         self.dlogit = torch.zeros(nmax, **f)
         self.loss = torch.zeros(max_groups + 1, **f)
+        self.head_counter = torch.zeros(1, device=device, dtype=torch.int32)
         self.labels_train = torch.tensor([1.0, 0.0][:max_groups], **f)
         self.labels_ones = torch.ones(max_groups, **f)
         self.img = torch.empty((nmax, *self.shape), **f)          # real || X_d
         self.feedback = torch.empty((batch_size, *self.shape), **f)
+        self._packs: Optional[ops.PackPlan] = None
         self.repack()
 
     # ------------------------------------------------------------------ parameters
     def repack(self) -> None:
-        P = self.state.p
-        for l, ly in enumerate(self.L[:-1]):
-            if l >= 1:
-                ops.pack_up(P[ly.weight], self.wq[l])
-                ops.pack_down(P[ly.weight], self.wp[l])
-        ops.head_pack(P[self.L[-1].weight], self.w_head)
+        """One launch re-packs every tensor-core operand + the head weight from the (just updated) parameters."""
+        if self._packs is None:
+            P = self.state.p
+            plan = ops.PackPlan(self.device)
+            for l, ly in enumerate(self.L[:-1]):
+                if l >= 1:
+                    plan.add_up(P[ly.weight], self.wq[l])
+                    plan.add_down(P[ly.weight], self.wp[l])
+            plan.add_head(P[self.L[-1].weight], self.w_head.view(-1, self.L[-1].c_in))
+            self._packs = plan.finalize()
+        self._packs.run()
 
     def adam(self) -> None:
         s = self.state
@@ -207,8 +214,8 @@ class DiscNet:
                            G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope,
                            round_tf32=(self.rnd and L[l + 1].kind == "down"), eps=bn.eps, momentum=bn.momentum)
         head = L[-1]
-        ops.head_forward(self.a[-1][:n], self.w_head, labels, self.prob, self.loss_terms, self.dlogit, self.loss, G,
-                         b, head.k * head.k, head.c_in)
+        ops.head_forward(self.a[-1][:n], self.w_head, labels, self.prob, self.loss_terms, self.dlogit, self.loss,
+                         self.head_counter, G, b, head.k * head.k, head.c_in)
 
     def backward(self, img: torch.Tensor, G: int, train: bool, out: Optional[torch.Tensor] = None,
                  accumulate: bool = False) -> None:
@@ -226,11 +233,12 @@ class DiscNet:
             ops.bn_backward(self.da[l][:n], self.z[l][:n], self.stats[l], self.dz[l][:n],
                             Gd[bn.weight] if train else None, Gd[bn.bias] if train else None, self.sums[l], self.bn_ws,
                             G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd)
-            if train:
-                splits = ops.wgrad_splits(n, Ho, Ho, ly.c_out, ly.c_in, ops.MODE_DOWN)
-                ops.wgrad_gemm(self.dz[l][:n], self.a[l - 1][:n], self.partial[l], (n, Ho, Ho), ops.MODE_DOWN, splits,
-                               precision=self.prec)
-                ops.wgrad_unpack(self.partial[l], Gd[ly.weight], ops.MODE_DOWN, splits, ly.c_out, ly.c_out, ly.c_in)
+            if train:  # weight gradient on the side stream, next to the data gradient below
+                with ops.side_branch():
+                    splits = ops.wgrad_splits(n, Ho, Ho, ly.c_out, ly.c_in, ops.MODE_DOWN)
+                    ops.wgrad_gemm(self.dz[l][:n], self.a[l - 1][:n], self.partial[l], (n, Ho, Ho), ops.MODE_DOWN,
+                                   splits, precision=self.prec)
+                    ops.wgrad_unpack(self.partial[l], Gd[ly.weight], ops.MODE_DOWN, splits, ly.c_out, ly.c_out, ly.c_in)
             ops.conv_gemm(self.dz[l][:n], self.wq[l], ops.MODE_UP, ly.c_in, self.da[l - 1][:n], (n, Ho, Ho), (Ho, Ho),
                           precision=self.prec)
         l0 = L[0]
@@ -238,6 +246,7 @@ class DiscNet:
                          round_tf32=(self.rnd and not train))
         if train:
             ops.thin_wgrad(self.dz[0][:n], img[:n], self.partial[0], Gd[l0.weight])
+            ops.join_side()
         else:
             ops.thin_up(self.dz[0][:n], P[l0.weight], self.feedback if out is None else out, accumulate=accumulate)
 
@@ -312,14 +321,19 @@ class GenNet:
                 self.partial.append(torch.empty(ops.thin_wgrad_slices(n, ly.h_in, ly.h_in) * ly.c_in * ly.c_out * 16, **f))
         self.X = torch.empty((n, *self.shape), **f)
         self.dXt = torch.empty((n, *self.shape), **f)
+        self._packs: Optional[ops.PackPlan] = None
         self.repack()
 
     def repack(self) -> None:
-        P, L = self.state.p, self.L
-        ops.pack_dense(P[L[0].weight], self.wp_dense)
-        for l in range(1, len(L) - 1):
-            ops.pack_up(P[L[l].weight], self.wq[l])
-            ops.pack_down(P[L[l].weight], self.wp_dg[l])
+        if self._packs is None:
+            P, L = self.state.p, self.L
+            plan = ops.PackPlan(self.device)
+            plan.add_dense(P[L[0].weight], self.wp_dense)
+            for l in range(1, len(L) - 1):
+                plan.add_up(P[L[l].weight], self.wq[l])
+                plan.add_down(P[L[l].weight], self.wp_dg[l])
+            self._packs = plan.finalize()
+        self._packs.run()
 
     def adam(self) -> None:
         s = self.state
@@ -352,7 +366,8 @@ class GenNet:
         n, P, Gd, L = self.n, self.state.p, self.state.g, self.L
         last = L[-1]
         ops.tanh_backward(s, self.X, self.dXt, scale)
-        ops.thin_wgrad(self.a[-1], self.dXt, self.partial[-1], Gd[last.weight])
+        with ops.side_branch():  # weight gradients run next to the data-gradient chain (ops.side_branch)
+            ops.thin_wgrad(self.a[-1], self.dXt, self.partial[-1], Gd[last.weight])
         ops.thin_down(self.dXt, P[last.weight], self.da[-1], act=ops.ACT_NONE)
         for l in range(len(L) - 2, -1, -1):
             ly, bn = L[l], L[l].bn
@@ -361,10 +376,11 @@ class GenNet:
                             self.bn_ws, 1, n * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd)
             if l >= 1:
                 hi = ly.h_in
-                splits = ops.wgrad_splits(n, hi, hi, ly.c_in, ly.c_out, ops.MODE_DOWN)
-                ops.wgrad_gemm(self.a[l - 1], self.dz[l], self.partial[l], (n, hi, hi), ops.MODE_DOWN, splits,
-                               precision=self.prec)
-                ops.wgrad_unpack(self.partial[l], Gd[ly.weight], ops.MODE_DOWN, splits, ly.c_in, ly.c_in, ly.c_out)
+                with ops.side_branch():
+                    splits = ops.wgrad_splits(n, hi, hi, ly.c_in, ly.c_out, ops.MODE_DOWN)
+                    ops.wgrad_gemm(self.a[l - 1], self.dz[l], self.partial[l], (n, hi, hi), ops.MODE_DOWN, splits,
+                                   precision=self.prec)
+                    ops.wgrad_unpack(self.partial[l], Gd[ly.weight], ops.MODE_DOWN, splits, ly.c_in, ly.c_in, ly.c_out)
                 ops.conv_gemm(self.dz[l], self.wp_dg[l], ops.MODE_DOWN, ly.c_in, self.da[l - 1], (n, hi, hi), (Ho, Ho),
                               precision=self.prec)
             else:
@@ -374,3 +390,4 @@ class GenNet:
                                precision=self.prec)
                 ops.wgrad_unpack(self.partial[0], Gd[ly.weight], ops.MODE_DENSE, splits, self.z_dim, self.zc, c2,
                                  N=ly.c_out, KK=self.kk)
+        ops.join_side()

@@ -195,6 +195,7 @@ def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: 
             engine.train_workers()
         else:
             engine.device_iteration()   # uploads + the captured G forward / D steps / feedback / G backward / Adam
+            engine.prefetch_next(epoch, last=(epoch == epochs - 1))  # next iteration's host inputs while the GPU works
         t2 = stamp()
         srow["end.recv_data"] = srow["start.agg_gradients"] = t2
         for n in local:

@@ -65,6 +65,49 @@ def _pad(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
+# ----------------------------------------------------------------------------- branch overlap (fork / join)
+# The weight gradient of a layer and the data gradient that feeds the next layer's backward are independent, so the
+# weight-gradient branch can run on a side stream (also inside a captured CUDA graph, where the fork/join become
+# graph edges).  Opt-in (MDGAN_OVERLAP=1): both GEMMs are already sized to one wave of one-CTA-per-SM tiles (split-K
+# in the weight gradient), so on B200 the overlapped step measured 0.607 ms against 0.592 ms on one stream (MNIST
+# shape, b = 64) and 2.52 against 2.54 ms (CelebA shape).
+_side_streams = {}
+_overlap = os.environ.get("MDGAN_OVERLAP", "0") == "1"
+
+
+class side_branch:
+    """with side_branch(): launches go to the device's side stream, ordered after everything already queued on the
+    current stream.  join_side() makes the current stream wait for the side stream."""
+
+    def __enter__(self):
+        self._ctx = None
+        if not _overlap:
+            return self
+        main = torch.cuda.current_stream()
+        key = main.device.index
+        side = _side_streams.get(key)
+        if side is None:
+            side = _side_streams[key] = torch.cuda.Stream(device=main.device)
+        side.wait_stream(main)
+        self._ctx = torch.cuda.stream(side)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+        return False
+
+
+def join_side() -> None:
+    if not _overlap:
+        return
+    main = torch.cuda.current_stream()
+    side = _side_streams.get(main.device.index)
+    if side is not None:
+        main.wait_stream(side)
+
+
 def n_pad_for(n: int) -> int:
     """Packed-weight row padding: a multiple of the narrowest tensor-core tile (16)."""
     return _pad(n, 16) if n < 32 else _pad(n, 32)
@@ -122,6 +165,59 @@ def pack_dense(W: torch.Tensor, out: Optional[torch.Tensor] = None, precision: i
          lambda: _lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 2, N, Cc, KK * N, Cp, KK, _split_of(out, KK * N),
                                                 _stream()))
     return out
+
+
+class PackPlan:
+    """All weight re-packs of one network as ONE launch (mdgan_pack_weights_multi), issued after its Adam step."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.jobs = []      # rows of 11 ints
+        self.keep = []      # the tensors the recorded pointers refer to
+        self.blocks = 0
+        self.nbytes = 0.0
+        self.table: Optional[torch.Tensor] = None
+
+    def _add(self, W, out, mode, N, Cc, Np, Cp, KK, total, split):
+        if self.table is not None:
+            raise _lib.MdganLibraryError("PackPlan is already finalized")
+        _ptr(W), _ptr(out)  # CUDA + contiguous checks
+        self.jobs.append([W.data_ptr(), out.data_ptr(), mode, N, Cc, Np, Cp, KK, total, self.blocks, split])
+        self.keep += [W, out]
+        self.blocks += (total + 255) // 256
+        self.nbytes += 4.0 * (W.numel() + out.numel())
+
+    def add_down(self, W, out):
+        N, Cc = W.shape[0], W.shape[1]
+        Np, Cp = n_pad_for(N), _pad(Cc, 32)
+        self._add(W, out, 0, N, Cc, Np, Cp, 16, Np * 16 * Cp, _split_of(out, Np))
+
+    def add_up(self, W, out):
+        Cc, N = W.shape[0], W.shape[1]
+        Np, Cp = n_pad_for(N), _pad(Cc, 32)
+        self._add(W, out, 1, N, Cc, Np, Cp, 16, 4 * Np * 4 * Cp, _split_of(out, 4 * Np))
+
+    def add_dense(self, W, out):
+        Cc, N, KK = W.shape[0], W.shape[1], W.shape[2] * W.shape[3]
+        Cp = _pad(Cc, 32)
+        self._add(W, out, 2, N, Cc, KK * N, Cp, KK, KK * N * Cp, _split_of(out, KK * N))
+
+    def add_head(self, w, wt):
+        Cc, HW = w.shape[1], w.shape[2] * w.shape[3]
+        self._add(w, wt, 3, HW, Cc, HW, Cc, 1, HW * Cc, 0)
+
+    def finalize(self) -> "PackPlan":
+        words = _lib.load().mdgan_pack_job_words()
+        if any(len(j) != words for j in self.jobs):
+            raise _lib.MdganLibraryError("pack job record size mismatch with the library")
+        self.table = torch.tensor(self.jobs, dtype=torch.int64).to(self.device)
+        return self
+
+    def run(self) -> None:
+        if self.table is None:
+            self.finalize()
+        _run("pack_weights", 1, 0, self.nbytes,
+             lambda: _lib.load().mdgan_pack_weights_multi(_ptr(self.table), len(self.jobs), self.blocks, _stream()))
 
 
 # ----------------------------------------------------------------------------- tensor-core GEMMs
@@ -251,10 +347,11 @@ def head_pack(w, wt):
     return wt
 
 
-def head_forward(a, w, label, prob, loss_terms, dlogit, loss, G, b, HW, Cc):
-    _run("head_forward", 2, 2.0 * G * b * HW * Cc, 4.0 * (G * b * HW * Cc + HW * Cc),
+def head_forward(a, w, label, prob, loss_terms, dlogit, loss, counter, G, b, HW, Cc):
+    """counter: one zero-initialised int32 device scalar (block counter of the fused loss reduction)."""
+    _run("head_forward", 1, 2.0 * G * b * HW * Cc, 4.0 * (G * b * HW * Cc + HW * Cc),
          lambda: _lib.load().mdgan_head_forward(_ptr(a), _ptr(w), _ptr(label), _ptr(prob), _ptr(loss_terms),
-                                                _ptr(dlogit), _ptr(loss), G, b, HW, Cc, _stream()))
+                                                _ptr(dlogit), _ptr(loss), _ptr(counter), G, b, HW, Cc, _stream()))
 
 
 def head_backward(a, w, dlogit, da, dw, n_total, HW, Cc):
@@ -264,7 +361,10 @@ def head_backward(a, w, dlogit, da, dw, n_total, HW, Cc):
 
 
 def adam_step(p, g, m, v, step_count, lr, beta1, beta2, eps=1e-8):
-    _run("adam_step", 2, 0, 28.0 * p.numel(),
+    """step_count: int32 [2] on the device = (steps taken, zero-initialised block counter)."""
+    if step_count.numel() < 2:
+        raise _lib.MdganLibraryError("adam_step: step_count must hold 2 int32 (step, block counter)")
+    _run("adam_step", 1, 0, 28.0 * p.numel(),
          lambda: _lib.load().mdgan_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(step_count), lr, beta1,
                                              beta2, eps, _stream()))
 

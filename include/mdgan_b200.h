@@ -56,6 +56,11 @@ int mdgan_check_device(void);
  * hi = tf32(w) and lo = tf32(w - hi). */
 int mdgan_pack_weights(const float* W, float* out, int mode, int N, int C, int N_pad, int C_pad, int KK, int split,
                        void* stream);
+/* All re-packs of one network in one launch.  jobs_dev: n_jobs records of mdgan_pack_job_words() (= 11) int64 words in
+ * DEVICE memory: {W ptr, out ptr, mode, N, C, N_pad, C_pad, KK, total elements of the hi matrix, first block, split};
+ * job j owns blocks [first_block_j, first_block_{j+1}) of 256 threads; mode 3 = mdgan_head_pack (N = HW, no rounding). */
+int mdgan_pack_job_words(void);
+int mdgan_pack_weights_multi(const long long* jobs_dev, int n_jobs, int total_blocks, void* stream);
 
 /* ---- implicit-GEMM convolution, tcgen05 (kind::tf32) + TMEM + TMA ---------------------------------------------
  * src  NHWC [n_img][Hs][Ws][C] (C % 32 == 0), wpacked from mdgan_pack_weights, rows = the low-resolution grid
@@ -125,16 +130,18 @@ int mdgan_tanh_backward(const float* s, const float* x, float* out, long long n,
  * a NHWC [G*b][HW][C]; wt [HW][C] = the PyTorch weight [1][C][k][k] re-ordered by mdgan_head_pack (once per
  * optimiser step); label[g] in {0,1}; dw is written in the PyTorch layout.  prob/loss_terms/dlogit are [G*b];
  * loss[g] = mean BCE of pass g (log clamped at -100), loss[G] = sum over passes.  dlogit already contains 1/b and
- * BCELoss' max(p(1-p), 1e-12) guard.
+ * BCELoss' max(p(1-p), 1e-12) guard.  counter: one device uint32, zero before the first call (the last block to
+ * finish reduces the per-sample terms into loss[] in a fixed order and clears it again).
  * Replaces CIFAR10.py:96-97,106 / CelebA.py:91-93,100-101 and nn.BCELoss actors/worker.py:96,199-204,222-227. */
 int mdgan_head_pack(const float* w, float* wt, int HW, int C, void* stream);
 int mdgan_head_forward(const float* a, const float* wt, const float* label, float* prob, float* loss_terms,
-                       float* dlogit, float* loss, int G, int b, int HW, int C, void* stream);
+                       float* dlogit, float* loss, unsigned int* counter, int G, int b, int HW, int C, void* stream);
 int mdgan_head_backward(const float* a, const float* wt, const float* dlogit, float* da, float* dw, int n_total, int HW,
                         int C, void* stream);
 
 /* ---- torch.optim.Adam on a flat parameter buffer (actors/server.py:111-113,308-312; actors/worker.py:97-99,206).
- * step_count is a device int32 holding the number of steps already taken; it is incremented on the device. */
+ * step_count points to two device int32: [0] the number of steps already taken (incremented on the device by the
+ * last block of the launch), [1] a block counter that must be zero before the first call. */
 int mdgan_adam_step(float* p, const float* g, float* m, float* v, long long n, int* step_count, float lr, float beta1,
                     float beta2, float eps, void* stream);
 

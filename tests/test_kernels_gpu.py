@@ -229,7 +229,11 @@ def test_head_bce(ops, dev, C, k):
     loss = torch.zeros(G + 1, device=dev)
     a_d = nhwc(a).to(dev)
     wt = ops.head_pack(w.to(dev), torch.empty(k * k * C, device=dev))
-    ops.head_forward(a_d, wt, labels.to(dev), prob, terms, dlogit, loss, G, b, k * k, C)
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    for _ in range(2):  # twice: the fused loss reduction must leave its block counter cleared
+        loss.zero_()
+        ops.head_forward(a_d, wt, labels.to(dev), prob, terms, dlogit, loss, counter, G, b, k * k, C)
+    assert int(counter.item()) == 0
     da, dw = torch.empty_like(a_d), torch.empty_like(w, device=dev)
     ops.head_backward(a_d, wt, dlogit, da, dw, G * b, k * k, C)
     assert relerr(prob, p) < 1e-5
@@ -237,20 +241,39 @@ def test_head_bce(ops, dev, C, k):
     assert relerr(nchw(da), ad.grad) < 1e-4 and relerr(dw, wd.grad) < 1e-4
 
 
+@pytest.mark.parametrize("prec", [0, 1])
+def test_pack_plan_matches_single_packs(ops, dev, prec):
+    """One mdgan_pack_weights_multi launch == the individual pack launches, bit for bit (incl. the head re-order)."""
+    torch.manual_seed(21)
+    Wd, Wu = torch.randn(128, 64, 4, 4, device=dev), torch.randn(256, 128, 4, 4, device=dev)
+    Wz, Wh = torch.randn(100, 96, 7, 7, device=dev), torch.randn(1, 128, 7, 7, device=dev)
+    ref = [ops.pack_down(Wd, precision=prec), ops.pack_up(Wu, precision=prec), ops.pack_dense(Wz, precision=prec),
+           ops.head_pack(Wh, torch.empty(49 * 128, device=dev))]
+    outs = [torch.full_like(r, float("nan")) for r in ref]
+    plan = ops.PackPlan(dev)
+    plan.add_down(Wd, outs[0])
+    plan.add_up(Wu, outs[1])
+    plan.add_dense(Wz, outs[2])
+    plan.add_head(Wh, outs[3])
+    plan.finalize().run()
+    for o, r in zip(outs, ref):
+        assert torch.equal(o, r)
+
+
 def test_adam_matches_torch(ops, dev):
     torch.manual_seed(10)
-    n = 10007
+    n = 10007   # not a multiple of 4: float4 body + scalar tail
     p0 = torch.randn(n)
     ref = torch.nn.Parameter(p0.clone())
     opt = torch.optim.Adam([ref], lr=2e-4, betas=(0.5, 0.999))
     p, m, v = p0.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
-    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    step = torch.zeros(2, dtype=torch.int32, device=dev)   # (steps taken, block counter)
     for it in range(5):
         g = torch.randn(n) * (10.0 ** (-it))
         ref.grad = g.clone()
         opt.step()
         ops.adam_step(p, g.to(dev), m, v, step, 2e-4, 0.5, 0.999)
-    assert int(step.item()) == 5
+    assert step.tolist() == [5, 0]
     assert (p.cpu() - ref.data).abs().max().item() < 2e-7
 
 

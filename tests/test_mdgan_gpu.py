@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
     ("MNIST_DCGAN", 2, 16, 3, 10**6),    # BASELINE config 2 shape
     ("CelebA", 2, 8, 3, 1),
     ("CelebA", 8, 8, 2, 1),              # BASELINE config 4 shape: N = 8 (k = 2)
+    ("CIFAR10", 2, 10, 3, 2),            # the reference's default batch size (shared-args.sh: batch_size=10), ragged tiles
 ])
 def test_engine_matches_oracle(name, n_workers, b, epochs, swap):
     r = run_engine_vs_oracle(name, n_workers, b, epochs, swap, mode="trajectory")
