@@ -20,7 +20,7 @@ _ll = C.c_longlong
 SIGNATURES = {
     "mdgan_abi_version": (_i, []),
     "mdgan_check_device": (_i, []),
-    "mdgan_conv_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mdgan_conv_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _f, _p]),
     "mdgan_wgrad_splits": (_i, [_i, _i, _i, _i, _i, _i]),
     "mdgan_wgrad_gemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_debug_set_wgrad_desc": (None, [_i, _i]),
@@ -30,8 +30,8 @@ SIGNATURES = {
     "mdgan_pack_weights_multi": (_i, [_p, _i, _i, _p]),
     "mdgan_reduce_slices": (_i, [_p, _p, _i, _ll, _p]),
     "mdgan_bn_workspace_floats": (_ll, [_i, _i, _i]),
-    "mdgan_bn_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _f, _i, _p]),
-    "mdgan_bn_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
+    "mdgan_bn_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _f, _i, _p]),
+    "mdgan_bn_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "mdgan_act_backward": (_i, [_p, _p, _p, _ll, _i, _f, _i, _p]),
     "mdgan_tanh_backward": (_i, [_p, _p, _p, _ll, _f, _p]),
     "mdgan_head_pack": (_i, [_p, _p, _i, _i, _p]),

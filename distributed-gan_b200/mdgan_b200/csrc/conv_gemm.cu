@@ -42,13 +42,19 @@ struct ConvGemmParams {
   int round_tf32;     // 1: store outputs rounded to TF32 (they feed another tensor-core operand)
   int accumulate;     // 1: dst += result (NCHW outputs only; sums feedbacks of workers sharing a batch)
   int lo_row_offset;  // tf32x3: row offset of the `lo` half of the packed weights
+  const float* gate;  // optional, NHWC like dst: dst = result * act'(gate) (backward of the activation that produced
+  int gate_act;       //   `gate`, fused into the data-gradient GEMM that feeds it; 1 ReLU, 2 LeakyReLU(gate_slope))
+  float gate_slope;
 };
 
 constexpr int kBM = 128;
 constexpr int kBK = 32;  // fp32 elements per K step = 128 bytes
 constexpr int kNumProducerWarps = 8;
 constexpr int kThreads = (kNumProducerWarps + 2) * 32;
-constexpr int kPrefetch = 4;  // K steps of activation loads kept in flight in registers per producer thread
+#ifndef MDGAN_CONV_PREFETCH
+#define MDGAN_CONV_PREFETCH 4
+#endif
+constexpr int kPrefetch = MDGAN_CONV_PREFETCH;  // K steps of activation loads kept in flight in registers per producer thread
 
 template <int BN, int STAGES, bool X3>
 struct ConvGemmSmem {
@@ -106,7 +112,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
   pdl_trigger();  // the next kernel's CTAs may take SMs as they drain; it waits for this grid before touching memory
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], kNumProducerWarps * 32 + 1);
+      mbar_init(&full_bar[s], kNumProducerWarps + 1);  // one arrive per producer warp + the TMA thread
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -184,8 +190,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
                      // the dropped lo*lo term is ~2^-22 relative
               sts128(a_stage + S::kHalfBytes + soff[i], v.x - hx, v.y - hy, v.z - hz, v.w - hw);
           }
-          fence_proxy_async_smem();
-          mbar_arrive(&full_bar[s]);
+          fence_proxy_async_smem();  // every thread publishes its own stores to the async proxy ...
+          __syncwarp();              // ... the warp agrees they are all done, and one lane arrives for the 32
+          if (lane == 0) mbar_arrive(&full_bar[s]);
           if (it + kPrefetch < ksteps) issue_loads(buf[u]);
           if (++s == STAGES) { s = 0; par ^= 1; }
         }
@@ -234,15 +241,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
           v[j] = x;
         }
         if (!p.out_nchw) {
-          float* o = p.dst + (static_cast<size_t>((img * Ho + oh) * Wo + ow)) * p.N + nbase;
+          const size_t oidx = (static_cast<size_t>((img * Ho + oh) * Wo + ow)) * p.N + nbase;
+          float* o = p.dst + oidx;
           if (nbase + 16 <= p.N && (p.N & 3) == 0) {
+            if (p.gate != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p.gate + oidx + j));
+                const float neg = p.gate_act == 2 ? p.gate_slope : 0.f;
+                v[j] *= a.x > 0.f ? 1.f : neg;
+                v[j + 1] *= a.y > 0.f ? 1.f : neg;
+                v[j + 2] *= a.z > 0.f ? 1.f : neg;
+                v[j + 3] *= a.w > 0.f ? 1.f : neg;
+                if (p.round_tf32) {
+                  v[j] = round_to_tf32(v[j]); v[j + 1] = round_to_tf32(v[j + 1]);
+                  v[j + 2] = round_to_tf32(v[j + 2]); v[j + 3] = round_to_tf32(v[j + 3]);
+                }
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
               *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (nbase + j < p.N) o[j] = v[j];
+              if (nbase + j < p.N) {
+                float x = v[j];
+                if (p.gate != nullptr) {
+                  x *= __ldg(p.gate + oidx + j) > 0.f ? 1.f : (p.gate_act == 2 ? p.gate_slope : 0.f);
+                  if (p.round_tf32) x = round_to_tf32(x);
+                }
+                o[j] = x;
+              }
           }
         } else {
 #pragma unroll
@@ -343,8 +373,10 @@ using namespace mdgan;
 // See include/mdgan_b200.h for the contract.
 extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img,
                                int Hg, int Wg, int Hs, int Ws, int C, int mode, int N, int N_pad, int out_nchw,
-                               int act, int round_tf32, int accumulate, int precision, int force_bn, void* stream) {
+                               int act, int round_tf32, int accumulate, int precision, int force_bn, const float* gate,
+                               int gate_act, float gate_slope, void* stream) {
   if (!src || !wpacked || !dst) return MDGAN_ERR_BAD_ARG;
+  if (gate && (out_nchw || (gate_act != 1 && gate_act != 2))) return MDGAN_ERR_UNSUPPORTED;
   if (C <= 0 || C % kBK != 0 || mode < 0 || mode > 2) return MDGAN_ERR_UNSUPPORTED;
   if (N_pad % 16 != 0 || N > N_pad || N <= 0) return MDGAN_ERR_UNSUPPORTED;
   ConvGemmParams p{};
@@ -354,6 +386,7 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   p.M = n_img * Hg * Wg;
   p.round_tf32 = round_tf32;
   p.accumulate = accumulate;
+  p.gate = gate; p.gate_act = gate_act; p.gate_slope = gate_slope;
   if (accumulate && !out_nchw) return MDGAN_ERR_UNSUPPORTED;
   if (p.M <= 0) return MDGAN_ERR_BAD_ARG;
   const int taps = mode == 0 ? 16 : (mode == 1 ? 4 : 1);

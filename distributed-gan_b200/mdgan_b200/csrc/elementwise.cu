@@ -149,83 +149,111 @@ __global__ void __launch_bounds__(256) reduce_slices_kernel(const float* __restr
 }
 
 // ----------------------------------------------------------------------------------------------- BatchNorm (train)
-// x is [G*Pg, C] (G independent passes of Pg rows each, e.g. real || X_d).  Stage 1: per-chunk partial sums.
-__global__ void bn_partial_kernel(const float* __restrict__ x, float* __restrict__ partial, int Pg, int C,
-                                  int chunks_per_group, int rows_per_chunk) {
+// x is [G*Pg, C] (G independent passes of Pg rows each, e.g. real || X_d).  Statistics kernel: grid = (G * chunks,
+// C / 32); a block reduces rows_per_chunk rows of one 32-channel slab (256 threads = 32 row lanes x 8 float4 quads)
+// into partial[chunk][2][C]; the LAST block of a slab to finish (device counter per slab) finalizes its 32 channels:
+// per group (in order) mean / biased var -> scale, shift; running stats with momentum and unbiased variance;
+// num_batches_tracked += G.  stats layout: [G][4][C] = mean, invstd, scale, shift.
+constexpr int kBnSlab = 32;
+
+__device__ __forceinline__ void bn_block_reduce(float (&s)[4], float (&ss)[4], float* sm, float* __restrict__ partial_row,
+                                                int slab, int C) {
+  // sm: [32 row lanes][2][32]
+  const int q = threadIdx.x & 7, rl = threadIdx.x >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sm[(rl * 2 + 0) * kBnSlab + q * 4 + j] = s[j];
+    sm[(rl * 2 + 1) * kBnSlab + q * 4 + j] = ss[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kBnSlab) {
+    const int stat = threadIdx.x >> 5, ch = threadIdx.x & 31;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) acc += sm[(l * 2 + stat) * kBnSlab + ch];
+    partial_row[stat * C + slab * kBnSlab + ch] = acc;
+  }
+}
+
+// true in every thread of the last block of this slab to arrive (all partials of the slab are then visible)
+__device__ __forceinline__ bool bn_last_block(unsigned int* counters, int slab) {
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(counters + slab, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    if (threadIdx.x == 0) counters[slab] = 0;
+  }
+  return last;
+}
+
+// sum over the chunks of group g of partial[.][stat 0/1][c]: 8 lanes (lane & 7) per channel, fp64, butterfly
+__device__ __forceinline__ void bn_chunk_sums(const float* __restrict__ partial, int g, int chunks_per_group, int C,
+                                              int c, double& s, double& ss) {
+  const int cl = threadIdx.x & 7;
+  s = 0.0;
+  ss = 0.0;
+  const float* pg = partial + (long long)g * chunks_per_group * 2 * C + c;
+#pragma unroll 4
+  for (int ch = cl; ch < chunks_per_group; ch += 8) {
+    s += __ldcg(pg + (long long)ch * 2 * C);
+    ss += __ldcg(pg + (long long)ch * 2 * C + C);
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const float* __restrict__ x, float* __restrict__ partial, unsigned int* __restrict__ counters,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ running_mean,
+                float* __restrict__ running_var, long long* __restrict__ nbt, float* __restrict__ stats, int G, int Pg,
+                int C, int chunks_per_group, int rows_per_chunk, float eps, float momentum) {
+  __shared__ float sm[32 * 2 * kBnSlab];
   pdl_enter();
-  extern __shared__ float sm[];  // [row_lanes][2][C]
-  const int quads = C >> 2;
-  const int row_lanes = blockDim.x / quads;
-  const int q = threadIdx.x % quads, rl = threadIdx.x / quads;
+  const int slab = blockIdx.y;
+  const int q = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int g = blockIdx.x / chunks_per_group, ch = blockIdx.x % chunks_per_group;
   const int r0 = ch * rows_per_chunk;
   const int r1 = min(Pg, r0 + rows_per_chunk);
   float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-  if (rl < row_lanes) {
-    const float* base = x + ((long long)g * Pg) * C + q * 4;
-    for (int r = r0 + rl; r < r1; r += row_lanes) {
-      const float4 v = *reinterpret_cast<const float4*>(base + (long long)r * C);
-      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-      ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sm[(rl * 2 + 0) * C + q * 4 + j] = s[j];
-      sm[(rl * 2 + 1) * C + q * 4 + j] = ss[j];
-    }
+  const float* base = x + ((long long)g * Pg) * C + slab * kBnSlab + q * 4;
+#pragma unroll 4
+  for (int r = r0 + rl; r < r1; r += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(base + (long long)r * C);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float acc = 0.f;
-    for (int l = 0; l < row_lanes; ++l) acc += sm[l * 2 * C + i];
-    partial[(long long)blockIdx.x * 2 * C + i] = acc;
-  }
-}
-
-// Stage 2: per group (in order) mean / biased var -> scale, shift; running stats with momentum 0.1 and unbiased
-// variance, num_batches_tracked += G.  stats layout: [G][4][C] = mean, invstd, scale, shift.
-// One warp per channel: the lanes stride the chunk partials (independent loads), fp64 butterfly reduction.
-__global__ void __launch_bounds__(256)
-bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma, const float* __restrict__ beta,
-                   float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
-                   float* __restrict__ stats, int G, int Pg, int C, int chunks_per_group, float eps, float momentum) {
-  pdl_enter();
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += G;
-  if (c >= C) return;
+  bn_block_reduce(s, ss, sm, partial + (long long)blockIdx.x * 2 * C, slab, C);
+  if (!bn_last_block(counters, slab)) return;
+  if (slab == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += G;
+  const int c = slab * kBnSlab + (threadIdx.x >> 3);  // 8 lanes per channel
   float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
   const float gm = gamma[c], bt = beta[c];
-  for (int g = 0; g < G; ++g) {
-    double s = 0.0, ss = 0.0;
-    const float* pg = partial + (long long)g * chunks_per_group * 2 * C + c;
-#pragma unroll 4
-    for (int ch = lane; ch < chunks_per_group; ch += 32) {
-      s += pg[(long long)ch * 2 * C];
-      ss += pg[(long long)ch * 2 * C + C];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    }
-    const double mean = s / Pg;
-    double var = ss / Pg - mean * mean;
+  for (int gi = 0; gi < G; ++gi) {
+    double sum, sq;
+    bn_chunk_sums(partial, gi, chunks_per_group, C, c, sum, sq);
+    const double mean = sum / Pg;
+    double var = sq / Pg - mean * mean;
     if (var < 0.0) var = 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)eps));
     const float sc = gm * invstd;
     const float unbiased = (float)(var * ((double)Pg / (double)(Pg > 1 ? Pg - 1 : 1)));
     rm = (1.f - momentum) * rm + momentum * (float)mean;
     rv = (1.f - momentum) * rv + momentum * unbiased;
-    if (lane == 0) {
-      float* st = stats + (long long)g * 4 * C;
+    if ((threadIdx.x & 7) == 0) {
+      float* st = stats + (long long)gi * 4 * C;
       st[c] = (float)mean;
       st[C + c] = invstd;
       st[2 * C + c] = sc;
       st[3 * C + c] = bt - (float)mean * sc;
     }
   }
-  if (lane == 0) {
+  if ((threadIdx.x & 7) == 0) {
     if (running_mean) running_mean[c] = rm;
     if (running_var) running_var[c] = rv;
   }
@@ -265,26 +293,29 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
   *reinterpret_cast<float4*>(out + e) = o;
 }
 
-// Backward stage 1: dy = da * act'(y); partial sums of dy and dy*xhat per channel.
-__global__ void bn_bwd_partial_kernel(const float* __restrict__ da, const float* __restrict__ x,
-                                      const float* __restrict__ stats, float* __restrict__ partial, int Pg, int C,
-                                      int chunks_per_group, int rows_per_chunk, int act, float slope) {
+// Backward statistics (same grid / last-block scheme as bn_stats_kernel): dy = da * act'(y); per channel
+// sums[g][2][C] = (sum dy, sum dy*xhat); dgamma / dbeta = totals over all groups (optional).
+__global__ void __launch_bounds__(256)
+bn_bwd_stats_kernel(const float* __restrict__ da, const float* __restrict__ x, const float* __restrict__ stats,
+                    float* __restrict__ partial, unsigned int* __restrict__ counters, float* __restrict__ sums,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int Pg, int C, int chunks_per_group,
+                    int rows_per_chunk, int act, float slope) {
+  __shared__ float sm[32 * 2 * kBnSlab];
   pdl_enter();
-  extern __shared__ float sm[];
-  const int quads = C >> 2;
-  const int row_lanes = blockDim.x / quads;
-  const int q = threadIdx.x % quads, rl = threadIdx.x / quads;
+  const int slab = blockIdx.y;
+  const int q = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int g = blockIdx.x / chunks_per_group, ch = blockIdx.x % chunks_per_group;
   const int r0 = ch * rows_per_chunk;
   const int r1 = min(Pg, r0 + rows_per_chunk);
   float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-  if (rl < row_lanes) {
-    const float* st = stats + (long long)g * 4 * C + q * 4;
+  {
+    const float* st = stats + (long long)g * 4 * C + slab * kBnSlab + q * 4;
     float mean[4], invstd[4], sc[4], sh[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { mean[j] = st[j]; invstd[j] = st[C + j]; sc[j] = st[2 * C + j]; sh[j] = st[3 * C + j]; }
-    const long long base = ((long long)g * Pg) * C + q * 4;
-    for (int r = r0 + rl; r < r1; r += row_lanes) {
+    const long long base = ((long long)g * Pg) * C + slab * kBnSlab + q * 4;
+#pragma unroll 2
+    for (int r = r0 + rl; r < r1; r += 32) {
       const float4 xv = *reinterpret_cast<const float4*>(x + base + (long long)r * C);
       const float4 dv = *reinterpret_cast<const float4*>(da + base + (long long)r * C);
       const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -297,51 +328,22 @@ __global__ void bn_bwd_partial_kernel(const float* __restrict__ da, const float*
         ss[j] += dy * ((xs[j] - mean[j]) * invstd[j]);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sm[(rl * 2 + 0) * C + q * 4 + j] = s[j];
-      sm[(rl * 2 + 1) * C + q * 4 + j] = ss[j];
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float acc = 0.f;
-    for (int l = 0; l < row_lanes; ++l) acc += sm[l * 2 * C + i];
-    partial[(long long)blockIdx.x * 2 * C + i] = acc;
-  }
-}
-
-// Backward stage 2: sums[g][2][C] (sum dy, sum dy*xhat); dgamma/dbeta = totals over all groups (optional).
-// One warp per channel, as bn_finalize_kernel.
-__global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, int G, int C, int chunks_per_group) {
-  pdl_enter();
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= C) return;
+  bn_block_reduce(s, ss, sm, partial + (long long)blockIdx.x * 2 * C, slab, C);
+  if (!bn_last_block(counters, slab)) return;
+  const int c = slab * kBnSlab + (threadIdx.x >> 3);
   double tg = 0.0, tb = 0.0;
-  for (int g = 0; g < G; ++g) {
-    double s = 0.0, ss = 0.0;
-    const float* pg = partial + (long long)g * chunks_per_group * 2 * C + c;
-#pragma unroll 4
-    for (int ch = lane; ch < chunks_per_group; ch += 32) {
-      s += pg[(long long)ch * 2 * C];
-      ss += pg[(long long)ch * 2 * C + C];
+  for (int gi = 0; gi < G; ++gi) {
+    double sum, sq;
+    bn_chunk_sums(partial, gi, chunks_per_group, C, c, sum, sq);
+    if ((threadIdx.x & 7) == 0) {
+      sums[(long long)gi * 2 * C + c] = (float)sum;
+      sums[(long long)gi * 2 * C + C + c] = (float)sq;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    }
-    if (lane == 0) {
-      sums[(long long)g * 2 * C + c] = (float)s;
-      sums[(long long)g * 2 * C + C + c] = (float)ss;
-    }
-    tb += s;
-    tg += ss;
+    tb += sum;
+    tg += sq;
   }
-  if (lane == 0) {
+  if ((threadIdx.x & 7) == 0) {
     if (dgamma) dgamma[c] = (float)tg;
     if (dbeta) dbeta[c] = (float)tb;
   }
@@ -625,9 +627,11 @@ extern "C" int mdgan_reduce_slices(const float* partial, float* out, int slices,
   return 0;
 }
 
-// Chunking shared by the BN forward and backward reductions: enough blocks to cover the machine, whole rows.
-static void bn_chunks(int Pg, int G, int* chunks_per_group, int* rows_per_chunk) {
-  int cpg = (296 + G - 1) / G;
+// Chunking shared by the BN forward and backward reductions: about four blocks per SM over (chunks x 32-channel
+// slabs), at least 32 rows per chunk.
+static void bn_chunks(int Pg, int G, int C, int* chunks_per_group, int* rows_per_chunk) {
+  const int slabs = C / 32 > 0 ? C / 32 : 1;
+  int cpg = 592 / (G * slabs);
   if (cpg > (Pg + 31) / 32) cpg = (Pg + 31) / 32;
   if (cpg < 1) cpg = 1;
   *rows_per_chunk = (Pg + cpg - 1) / cpg;
@@ -636,24 +640,21 @@ static void bn_chunks(int Pg, int G, int* chunks_per_group, int* rows_per_chunk)
 
 extern "C" long long mdgan_bn_workspace_floats(int G, int Pg, int C) {
   int cpg, rpc;
-  bn_chunks(Pg, G, &cpg, &rpc);
+  bn_chunks(Pg, G, C, &cpg, &rpc);
   return (long long)G * cpg * 2 * C;
 }
 
 extern "C" int mdgan_bn_forward(const float* x, float* out, const float* gamma, const float* beta, float* running_mean,
                                 float* running_var, long long* num_batches_tracked, float* stats, float* workspace,
-                                int G, int Pg, int C, float eps, float momentum, int act, float slope, int round_tf32,
-                                void* stream) {
-  if (!x || !out || !gamma || !beta || !stats || !workspace) return MDGAN_ERR_BAD_ARG;
-  if (C % 4 != 0 || C > 1024 || 256 % (C / 4) != 0) return MDGAN_ERR_UNSUPPORTED;
+                                unsigned int* counters, int G, int Pg, int C, float eps, float momentum, int act,
+                                float slope, int round_tf32, void* stream) {
+  if (!x || !out || !gamma || !beta || !stats || !workspace || !counters) return MDGAN_ERR_BAD_ARG;
+  if (C % 32 != 0 || C > 1024 || G < 1 || Pg < 1) return MDGAN_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   int cpg, rpc;
-  bn_chunks(Pg, G, &cpg, &rpc);
-  const int row_lanes = 256 / (C / 4);
-  MDGAN_LAUNCH(bn_partial_kernel, dim3(G * cpg), dim3(256), row_lanes * 2 * C * sizeof(float), st, x, workspace, Pg, C,
-               cpg, rpc);
-  MDGAN_LAUNCH(bn_finalize_kernel, dim3(blocks_for(C, 8)), dim3(256), 0, st, workspace, gamma, beta, running_mean,
-               running_var, num_batches_tracked, stats, G, Pg, C, cpg, eps, momentum);
+  bn_chunks(Pg, G, C, &cpg, &rpc);
+  MDGAN_LAUNCH(bn_stats_kernel, dim3(G * cpg, C / 32), dim3(256), 0, st, x, workspace, counters, gamma, beta, running_mean,
+               running_var, num_batches_tracked, stats, G, Pg, C, cpg, rpc, eps, momentum);
   const long long total4 = (long long)G * Pg * C / 4;
   MDGAN_LAUNCH(bn_apply_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, x, stats, out, Pg, C, total4, act, slope,
                round_tf32);
@@ -661,17 +662,15 @@ extern "C" int mdgan_bn_forward(const float* x, float* out, const float* gamma, 
 }
 
 extern "C" int mdgan_bn_backward(const float* da, const float* x, const float* stats, float* dx, float* dgamma,
-                                 float* dbeta, float* sums, float* workspace, int G, int Pg, int C, int act,
-                                 float slope, int round_tf32, void* stream) {
-  if (!da || !x || !stats || !dx || !sums || !workspace) return MDGAN_ERR_BAD_ARG;
-  if (C % 4 != 0 || C > 1024 || 256 % (C / 4) != 0) return MDGAN_ERR_UNSUPPORTED;
+                                 float* dbeta, float* sums, float* workspace, unsigned int* counters, int G, int Pg, int C,
+                                 int act, float slope, int round_tf32, void* stream) {
+  if (!da || !x || !stats || !dx || !sums || !workspace || !counters) return MDGAN_ERR_BAD_ARG;
+  if (C % 32 != 0 || C > 1024 || G < 1 || Pg < 1) return MDGAN_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   int cpg, rpc;
-  bn_chunks(Pg, G, &cpg, &rpc);
-  const int row_lanes = 256 / (C / 4);
-  MDGAN_LAUNCH(bn_bwd_partial_kernel, dim3(G * cpg), dim3(256), row_lanes * 2 * C * sizeof(float), st, da, x, stats,
-               workspace, Pg, C, cpg, rpc, act, slope);
-  MDGAN_LAUNCH(bn_bwd_finalize_kernel, dim3(blocks_for(C, 8)), dim3(256), 0, st, workspace, sums, dgamma, dbeta, G, C, cpg);
+  bn_chunks(Pg, G, C, &cpg, &rpc);
+  MDGAN_LAUNCH(bn_bwd_stats_kernel, dim3(G * cpg, C / 32), dim3(256), 0, st, da, x, stats, workspace, counters, sums, dgamma,
+               dbeta, G, Pg, C, cpg, rpc, act, slope);
   const long long total4 = (long long)G * Pg * C / 4;
   MDGAN_LAUNCH(bn_bwd_apply_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, da, x, stats, sums, dx, Pg, C, total4,
                act, slope, round_tf32);

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
   pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], kWProducerWarps * 32);
+      mbar_init(&full_bar[s], kWProducerWarps);  // one arrive per producer warp
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -179,8 +179,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
           for (int i = 0; i < 4; ++i) store_split<X3>(stage + a_soff[i], S::kHalfBytes, abuf[u][i]);
 #pragma unroll
           for (int i = 0; i < kBPasses; ++i) store_split<X3>(stage + b_soff[i], S::kHalfBytes, bbuf[u][i]);
-          fence_proxy_async_smem();
-          mbar_arrive(&full_bar[s]);
+          fence_proxy_async_smem();  // every thread publishes its own stores to the async proxy ...
+          __syncwarp();              // ... the warp agrees they are all done, and one lane arrives for the 32
+          if (lane == 0) mbar_arrive(&full_bar[s]);
           if (it + kWPrefetch < ksteps) issue_loads(abuf[u], bbuf[u]);
           if (++s == STAGES) { s = 0; par ^= 1; }
         }

@@ -162,6 +162,7 @@ class DiscNet:
                 self.wp.append(None)
                 self.partial.append(torch.empty(ops.thin_wgrad_slices(nmax, Ho, Ho) * Cc * ly.c_in * 16, **f))
         self.bn_ws = torch.empty(max(ws, 1), **f)
+        self.bn_cnt = ops.bn_counters(device)
         head = L[-1]
         self.w_head = torch.empty(head.k * head.k * head.c_in, **f)
         self.prob = torch.zeros(nmax, **f)
@@ -211,7 +212,7 @@ class DiscNet:
             bn = ly.bn
             ops.bn_forward(self.z[l][:n], self.a[l][:n], P[bn.weight], P[bn.bias], B[bn.running_mean], B[bn.running_var],
                            B[bn.num_batches_tracked] if bn.num_batches_tracked else None, self.stats[l], self.bn_ws,
-                           G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope,
+                           self.bn_cnt, G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope,
                            round_tf32=(self.rnd and L[l + 1].kind == "down"), eps=bn.eps, momentum=bn.momentum)
         head = L[-1]
         ops.head_forward(self.a[-1][:n], self.w_head, labels, self.prob, self.loss_terms, self.dlogit, self.loss,
@@ -232,18 +233,21 @@ class DiscNet:
             Ho, bn = ly.h_out, ly.bn
             ops.bn_backward(self.da[l][:n], self.z[l][:n], self.stats[l], self.dz[l][:n],
                             Gd[bn.weight] if train else None, Gd[bn.bias] if train else None, self.sums[l], self.bn_ws,
-                            G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd)
+                            self.bn_cnt, G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd)
             if train:  # weight gradient on the side stream, next to the data gradient below
                 with ops.side_branch():
                     splits = ops.wgrad_splits(n, Ho, Ho, ly.c_out, ly.c_in, ops.MODE_DOWN)
                     ops.wgrad_gemm(self.dz[l][:n], self.a[l - 1][:n], self.partial[l], (n, Ho, Ho), ops.MODE_DOWN,
                                    splits, precision=self.prec)
                     ops.wgrad_unpack(self.partial[l], Gd[ly.weight], ops.MODE_DOWN, splits, ly.c_out, ly.c_out, ly.c_in)
-            ops.conv_gemm(self.dz[l][:n], self.wq[l], ops.MODE_UP, ly.c_in, self.da[l - 1][:n], (n, Ho, Ho), (Ho, Ho),
-                          precision=self.prec)
+            if l == 1:  # the LeakyReLU backward of layer 0 rides in this GEMM's epilogue: dz[0] = dgrad * act'(a[0])
+                ops.conv_gemm(self.dz[l][:n], self.wq[l], ops.MODE_UP, ly.c_in, self.dz[0][:n], (n, Ho, Ho), (Ho, Ho),
+                              precision=self.prec, gate=self.a[0][:n], gate_act=ops.ACT_LRELU, gate_slope=L[0].slope,
+                              round_tf32=(self.rnd and not train))
+            else:
+                ops.conv_gemm(self.dz[l][:n], self.wq[l], ops.MODE_UP, ly.c_in, self.da[l - 1][:n], (n, Ho, Ho), (Ho, Ho),
+                              precision=self.prec)
         l0 = L[0]
-        ops.act_backward(self.da[0][:n], self.a[0][:n], self.dz[0][:n], ops.ACT_LRELU, l0.slope,
-                         round_tf32=(self.rnd and not train))
         if train:
             ops.thin_wgrad(self.dz[0][:n], img[:n], self.partial[0], Gd[l0.weight])
             ops.join_side()
@@ -301,6 +305,7 @@ class GenNet:
             self.sums.append(torch.zeros(2 * Cc, **f))
             ws = max(ws, ops.bn_workspace_floats(1, n * Ho * Ho, Cc))
         self.bn_ws = torch.empty(max(ws, 1), **f)
+        self.bn_cnt = ops.bn_counters(device)
         l0 = L[0]
         self.kk = l0.k * l0.k
         self.wp_dense = torch.empty(ops.packed_shape(ops.MODE_DENSE, l0.c_out, z_dim, self.kk, self.prec), **f)
@@ -355,7 +360,7 @@ class GenNet:
                               (ly.h_in, ly.h_in), precision=self.prec)
             ops.bn_forward(self.z[l], self.a[l], P[bn.weight], P[bn.bias], B[bn.running_mean], B[bn.running_var],
                            B[bn.num_batches_tracked] if bn.num_batches_tracked else None, self.stats[l], self.bn_ws,
-                           1, n * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd, eps=bn.eps,
+                           self.bn_cnt, 1, n * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd, eps=bn.eps,
                            momentum=bn.momentum)
         last = L[-1]
         ops.thin_up(self.a[-1], P[last.weight], self.X, act_tanh=True)
@@ -373,7 +378,7 @@ class GenNet:
             ly, bn = L[l], L[l].bn
             Ho = ly.h_out
             ops.bn_backward(self.da[l], self.z[l], self.stats[l], self.dz[l], Gd[bn.weight], Gd[bn.bias], self.sums[l],
-                            self.bn_ws, 1, n * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd)
+                            self.bn_ws, self.bn_cnt, 1, n * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd)
             if l >= 1:
                 hi = ly.h_in
                 with ops.side_branch():

@@ -224,9 +224,11 @@ class PackPlan:
 def conv_gemm(src: torch.Tensor, wpacked: torch.Tensor, mode: int, N: int, out: torch.Tensor,
               grid: Tuple[int, int, int], src_hw: Tuple[int, int], bias: Optional[torch.Tensor] = None,
               out_nchw: bool = False, act_tanh: bool = False, round_tf32: bool = False, accumulate: bool = False,
-              precision: int = TF32, force_bn: int = 0) -> torch.Tensor:
+              precision: int = TF32, force_bn: int = 0, gate: Optional[torch.Tensor] = None, gate_act: int = ACT_NONE,
+              gate_slope: float = 0.0) -> torch.Tensor:
     """grid = (n_img, Hg, Wg): the low-resolution row grid; src is NHWC [n_img, Hs, Ws, C].  With precision TF32X3
-    `wpacked` must hold the hi and lo matrices (pack_*(..., precision=TF32X3))."""
+    `wpacked` must hold the hi and lo matrices (pack_*(..., precision=TF32X3)).  gate (NHWC, shaped like out): the
+    result is multiplied by act'(gate) -- the (Leaky)ReLU backward fused into the data gradient that feeds it."""
     n_img, Hg, Wg = grid
     Hs, Ws = src_hw
     Cc = src.shape[-1]
@@ -238,7 +240,8 @@ def conv_gemm(src: torch.Tensor, wpacked: torch.Tensor, mode: int, N: int, out: 
     _run(("conv_down", "conv_up", "conv_dense")[mode], 1, flops, nbytes,
          lambda: _lib.load().mdgan_conv_gemm(_ptr(src), _ptr(wpacked), _ptr(out), _ptr(bias), n_img, Hg, Wg, Hs, Ws, Cc,
                                              mode, N, N_pad, int(out_nchw), int(act_tanh), int(round_tf32),
-                                             int(accumulate), precision, force_bn, _stream()))
+                                             int(accumulate), precision, force_bn, _ptr(gate), gate_act,
+                                             float(gate_slope), _stream()))
     return out
 
 
@@ -309,20 +312,28 @@ def bn_workspace_floats(G: int, Pg: int, Cc: int) -> int:
     return _lib.load().mdgan_bn_workspace_floats(G, Pg, Cc)
 
 
-def bn_forward(x, out, gamma, beta, running_mean, running_var, nbt, stats, workspace, G, Pg, Cc, act, slope,
+def bn_counters(device) -> torch.Tensor:
+    """The 32 zero-initialised slab counters mdgan_bn_forward / mdgan_bn_backward need (one tensor per net is enough:
+    launches on one stream use it one after the other and leave it zero)."""
+    return torch.zeros(32, dtype=torch.int32, device=device)
+
+
+def bn_forward(x, out, gamma, beta, running_mean, running_var, nbt, stats, workspace, counters, G, Pg, Cc, act, slope,
                round_tf32=False, eps=1e-5, momentum=0.1):
-    _run("bn_forward", 3, 0, 4.0 * 2 * G * Pg * Cc,
+    # algorithmic bytes: read x for the statistics, read x + write out for the normalisation
+    _run("bn_forward", 2, 0, 4.0 * 3 * G * Pg * Cc,
          lambda: _lib.load().mdgan_bn_forward(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(running_mean),
-                                              _ptr(running_var), _ptr(nbt), _ptr(stats), _ptr(workspace), G, Pg, Cc,
-                                              eps, momentum, act, slope, int(round_tf32), _stream()))
+                                              _ptr(running_var), _ptr(nbt), _ptr(stats), _ptr(workspace), _ptr(counters),
+                                              G, Pg, Cc, eps, momentum, act, slope, int(round_tf32), _stream()))
     return out
 
 
-def bn_backward(da, x, stats, dx, dgamma, dbeta, sums, workspace, G, Pg, Cc, act, slope, round_tf32=False):
-    _run("bn_backward", 3, 0, 4.0 * 3 * G * Pg * Cc,
+def bn_backward(da, x, stats, dx, dgamma, dbeta, sums, workspace, counters, G, Pg, Cc, act, slope, round_tf32=False):
+    # algorithmic bytes: read da + x for the sums, read da + x and write dx for the gradient
+    _run("bn_backward", 2, 0, 4.0 * 5 * G * Pg * Cc,
          lambda: _lib.load().mdgan_bn_backward(_ptr(da), _ptr(x), _ptr(stats), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                                               _ptr(sums), _ptr(workspace), G, Pg, Cc, act, slope, int(round_tf32),
-                                               _stream()))
+                                               _ptr(sums), _ptr(workspace), _ptr(counters), G, Pg, Cc, act, slope,
+                                               int(round_tf32), _stream()))
     return dx
 
 

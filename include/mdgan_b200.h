@@ -67,13 +67,16 @@ int mdgan_pack_weights_multi(const long long* jobs_dev, int n_jobs, int total_bl
  * (n_img, Hg, Wg).  Output: DOWN/DENSE -> [n_img][Hg][Wg][N]; UP -> [n_img][2Hg][2Wg][N]; NHWC, or NCHW when
  * out_nchw = 1 (image-side outputs).  bias (optional, [N]) is added, act = 1 applies tanh.  accumulate = 1 (NCHW only)
  * adds into dst: the feedbacks of all workers that share one generated batch are summed in place
- * (actors/server.py:271-297).  force_bn = 0 lets the launcher pick the tile width.
+ * (actors/server.py:271-297).  force_bn = 0 lets the launcher pick the tile width.  gate (optional, NHWC outputs only,
+ * same shape as dst): dst = result * act'(gate), gate_act = MDGAN_ACT_RELU / MDGAN_ACT_LRELU(gate_slope) -- the backward
+ * of the activation whose OUTPUT is `gate`, fused into the data-gradient GEMM that feeds it.
  * Replaces: nn.Conv2d(k4,s2,p1) forward CIFAR10.py:88,92 / CelebA.py:81,85,88; nn.ConvTranspose2d forward
  * CIFAR10.py:118-130 / CelebA.py:113-131 (+ torch.tanh CIFAR10.py:131 / CelebA.py:140); and their data
  * gradients computed by loss.backward() (actors/worker.py:204,227) and torch.autograd.grad (actors/server.py:286). */
 int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img, int Hg, int Wg,
                     int Hs, int Ws, int C, int mode, int N, int N_pad, int out_nchw, int act, int round_tf32,
-                    int accumulate, int precision, int force_bn, void* stream);
+                    int accumulate, int precision, int force_bn, const float* gate, int gate_act, float gate_slope,
+                    void* stream);
 
 /* ---- weight gradient, tcgen05 (kind::tf32, MN-major operands), split-K over pixels ----------------------------
  * partial[split][tap][C1][C2] = sum_p lo[p][c1] * hi[gather(p, tap)][c2]; mode DOWN = 16 taps of the k4 s2 p1
@@ -112,14 +115,17 @@ int mdgan_thin_wgrad(const float* feat, const float* img, float* partial, int n_
  * x [G*Pg][C]: G independent passes (e.g. real || X_d) of Pg = b*H*W rows; statistics per pass, running stats
  * updated once per pass in order (momentum, unbiased variance), *num_batches_tracked (int64) += G.
  * stats [G][4][C] = mean, invstd, scale, shift (kept for backward).  workspace: mdgan_bn_workspace_floats floats.
+ * counters: C/32 (<= 32) device uint32, zero before the first call and left zero by every call (the last block of a
+ * 32-channel slab to finish its partial sums finalizes that slab: 2 launches per pass instead of 3).  C % 32 == 0.
  * Replaces nn.BatchNorm2d + ReLU/LeakyReLU CIFAR10.py:89-94,119-128 / CelebA.py:97-99,134-137 and their backward. */
 long long mdgan_bn_workspace_floats(int G, int Pg, int C);
 int mdgan_bn_forward(const float* x, float* out, const float* gamma, const float* beta, float* running_mean,
-                     float* running_var, long long* num_batches_tracked, float* stats, float* workspace, int G, int Pg,
-                     int C, float eps, float momentum, int act, float slope, int round_tf32, void* stream);
+                     float* running_var, long long* num_batches_tracked, float* stats, float* workspace,
+                     unsigned int* counters, int G, int Pg, int C, float eps, float momentum, int act, float slope,
+                     int round_tf32, void* stream);
 int mdgan_bn_backward(const float* da, const float* x, const float* stats, float* dx, float* dgamma, float* dbeta,
-                      float* sums, float* workspace, int G, int Pg, int C, int act, float slope, int round_tf32,
-                      void* stream);
+                      float* sums, float* workspace, unsigned int* counters, int G, int Pg, int C, int act, float slope,
+                      int round_tf32, void* stream);
 int mdgan_act_backward(const float* da, const float* a, float* dz, long long n, int act, float slope, int round_tf32,
                        void* stream);
 /* out = s * (1 - x^2) * scale: backward of the generator's tanh on the group-summed feedback, with the

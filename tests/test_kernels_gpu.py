@@ -61,6 +61,20 @@ def test_conv_up(ops, dev, n, C, N, H, nchw_out, prec, tol):
     assert relerr(out if nchw_out else nchw(out), ref) < tol
 
 
+@pytest.mark.parametrize("N", [64, 128])
+def test_conv_up_gated(ops, dev, N):
+    """gate: the LeakyReLU backward of the layer below, fused into the data-gradient GEMM's epilogue."""
+    torch.manual_seed(14)
+    n, C, H = 5, 128, 7
+    x, W = torch.randn(n, C, H, H), torch.randn(C, N, 4, 4) * 0.05
+    a = torch.randn(n, N, 2 * H, 2 * H)  # the activation OUTPUT of the layer below (sign == sign of its input)
+    ref = F.conv_transpose2d(x.double(), W.double(), stride=2, padding=1) * torch.where(a > 0, 1.0, 0.2).double()
+    out = torch.empty(n, 2 * H, 2 * H, N, device=dev)
+    ops.conv_gemm(nhwc(x).to(dev), ops.pack_up(W.to(dev), precision=1), ops.MODE_UP, N, out, (n, H, H), (H, H), precision=1,
+                  gate=nhwc(a).to(dev), gate_act=ops.ACT_LRELU, gate_slope=0.2)
+    assert relerr(nchw(out), ref) < 2e-5
+
+
 def test_conv_up_accumulate(ops, dev):
     """accumulate=1: dst += result (how feedbacks of workers sharing a generated batch are summed)."""
     torch.manual_seed(12)
@@ -202,8 +216,10 @@ def test_batchnorm_fwd_bwd(ops, dev, G, b, H, C, act, slope):
     stats, sums = torch.zeros(G * 4 * C, device=dev), torch.zeros(G * 2 * C, device=dev)
     ws = torch.empty(ops.bn_workspace_floats(G, Pg, C), device=dev)
     dgamma, dbeta = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
-    ops.bn_forward(xd, out, gamma.to(dev), beta.to(dev), rm, rv, nbt, stats, ws, G, Pg, C, act, slope)
-    ops.bn_backward(nhwc(dout).to(dev), xd, stats, dx, dgamma, dbeta, sums, ws, G, Pg, C, act, slope)
+    cnt = ops.bn_counters(dev)
+    ops.bn_forward(xd, out, gamma.to(dev), beta.to(dev), rm, rv, nbt, stats, ws, cnt, G, Pg, C, act, slope)
+    ops.bn_backward(nhwc(dout).to(dev), xd, stats, dx, dgamma, dbeta, sums, ws, cnt, G, Pg, C, act, slope)
+    assert int(cnt.abs().sum().item()) == 0
     assert relerr(nchw(out), torch.cat(outs)) < FP32_TOL
     assert relerr(nchw(dx), torch.cat(dxs)) < 1e-4
     assert relerr(rm, bn.running_mean) < FP32_TOL and relerr(rv, bn.running_var) < FP32_TOL

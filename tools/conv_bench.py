@@ -29,7 +29,9 @@ print(f"precision {'tf32x3' if prec else 'tf32'} dbg {dbg}")
 layers = [("celebaD c2 down", 0, 128, 64, 128, 32), ("celebaD c3 down", 0, 128, 128, 256, 16), ("celebaD c4 down", 0, 128, 256, 512, 8),
           ("celebaG L2 up", 1, 128, 512, 256, 4), ("celebaG L3 up", 1, 128, 256, 128, 8), ("celebaG L4 up", 1, 128, 128, 64, 16),
           ("celebaG L5 up(nchw,3)", 1, 128, 64, 3, 32), ("mnistD c2 down", 0, 128, 64, 128, 14), ("mnistG L2 up", 1, 128, 256, 128, 7),
-          ("b1024 celebaD c3", 0, 2048, 128, 256, 16)]
+          ("b1024 celebaD c3", 0, 2048, 128, 256, 16),
+          ("mnistG dgrad L2 down", 0, 128, 128, 256, 14), ("mnistD dgrad c2 up", 1, 128, 128, 64, 7),
+          ("mnistD c2 fb down", 0, 64, 64, 128, 14), ("cifarD c3 down", 0, 128, 128, 256, 8), ("cifarG L3 up", 1, 128, 256, 128, 8)]
 only = os.environ.get('CONV_BENCH_ONLY')
 if only:
     layers = [l for l in layers if only in l[0]]
