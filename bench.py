@@ -390,6 +390,7 @@ def run_ours(args) -> None:
     roofline["launches_timed"] = a["calls"]
     roofline["share_of_step"] = a["ms"] / total_ms
     engine.close()
+    exchange_mode = getattr(engine.exchange, "mode", "nccl") if world > 1 else "none (one process)"
     shares = {n: {"share": round(v["ms"] / total_ms, 4), "us_per_iter": round(v["ms"] * 1e3 / 4, 2),
                   "calls_per_iter": v["calls"] // 4} for n, v in sorted(per_op.items(), key=lambda t: -t[1]["ms"])}
     del engine
@@ -440,7 +441,7 @@ def run_ours(args) -> None:
         "data": "synthetic",
         "config": {"workload": workload_name(args, n_workers), "dataset": args.dataset, "batch": b, "workers": n_workers,
                    "parallelism": f"one discriminator worker per GPU x{args.gpus}, generator on rank 0",
-                   "precision": args.precision, "cuda_graph": graphed,
+                   "precision": args.precision, "cuda_graph": graphed, "exchange": exchange_mode,
                    "l2": "512 MB buffer written between timed iterations (outside the per-step event pairs)",
                    "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,

@@ -40,6 +40,10 @@ SIGNATURES = {
     "mdgan_adam_step": (_i, [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _p]),
     "mdgan_pad_rows": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mdgan_sum_slices": (_i, [_p, _p, _ll, _i, _ll, _p]),
+    "mdgan_peer_signal": (_i, [_p, _i, _p, _i, _p]),
+    "mdgan_peer_wait": (_i, [_p, _i, _p, _i, _p, _p]),
+    "mdgan_peer_push": (_i, [_p, _p, _i, _ll, _p]),
+    "mdgan_tanh_backward_slices": (_i, [_p, _p, _p, _ll, _i, _i, _f, _p]),
     "mdgan_thin_down": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "mdgan_thin_up": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_thin_wgrad_slices": (_i, [_i, _i, _i]),

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import routing
-from .exchange import Exchange
+from .exchange import Exchange, make_exchange
 
 
 @dataclass
@@ -88,7 +88,8 @@ class MDGANEngine:
         if (generator is not None) != (proc == 0):
             raise ValueError("the generator lives on process 0 only")
         self.factory = factory or CudaNetFactory(device)
-        self.exchange = exchange or Exchange(proc, n_procs, self.N)
+        self.exchange = exchange or make_exchange(proc, n_procs, self.N, device, self.k, self.b, cfg.image_shape)
+        self.peer = getattr(self.exchange, "mode", "nccl") == "peer"
         kb = self.k * self.b
         self.gen = self.factory.generator(generator, cfg, kb) if proc == 0 else None
         self.disc = {n: self.factory.discriminator(discriminators[n], cfg) for n in self.local}
@@ -96,7 +97,9 @@ class MDGANEngine:
         self.gen_module = generator
         self.disc_modules = discriminators
         f = dict(device=device, dtype=torch.float32)
-        self.X = torch.zeros((kb, *cfg.image_shape), **f)
+        # peer mode: X is this process' symmetric copy (process 0 pushes into all of them) and the feedback goes to
+        # process 0's slice buffer F[n] instead of the summed S
+        self.X = self.exchange.X if self.peer else torch.zeros((kb, *cfg.image_shape), **f)
         self.S = torch.zeros((kb, *cfg.image_shape), **f)
         self.z = torch.zeros((kb, cfg.z_dim), **f)
         self.z_host = torch.zeros((kb, cfg.z_dim), dtype=torch.float32,
@@ -163,13 +166,17 @@ class MDGANEngine:
             if self.cfg.z_source != "host":
                 self.z.normal_()
             X = self.gen.forward(self.z)
+            if self.peer:
+                self.exchange.broadcast_fakes(X)  # push out of the net's buffer into every process' copy (+ flags)
+                return
             if X.data_ptr() != self.X.data_ptr():
                 self.X = X  # the net owns the [k*b, C, H, W] output buffer; broadcast straight out of it
         self.exchange.broadcast_fakes(self.X)
 
     def train_workers(self) -> None:
         k, b = self.k, self.b
-        self.S.zero_()
+        if not self.peer:
+            self.S.zero_()
         for i, n in enumerate(self.local):
             ig, id_ = routing.route(n, k)
             x_g, x_d = self.X[ig * b:(ig + 1) * b], self.X[id_ * b:(id_ + 1) * b]
@@ -177,13 +184,19 @@ class MDGANEngine:
             net = self.disc[n]
             for l in range(self.cfg.local_epochs):
                 self.d_loss[i, l].copy_(net.train_step(real, x_d))
-            slot = routing.feedback_slot(n, k)
-            self.g_loss[i].copy_(net.feedback_step(x_g, out=self.S[slot * b:(slot + 1) * b], accumulate=True))
+            if self.peer:  # the last data-gradient kernel stores into process 0's F[n] over NVLink
+                self.g_loss[i].copy_(net.feedback_step(x_g, out=self.exchange.feedback_slice(n), accumulate=False))
+            else:
+                slot = routing.feedback_slot(n, k)
+                self.g_loss[i].copy_(net.feedback_step(x_g, out=self.S[slot * b:(slot + 1) * b], accumulate=True))
         self.exchange.reduce_feedback(self.S)
 
     def update_generator(self) -> None:
         if self.proc == 0:
-            self.gen.backward(self.S, 1.0 / (self.b * self.N))
+            if self.peer:
+                self.gen.backward(None, 1.0 / (self.b * self.N), slices=(self.exchange.F, self.k, self.N))
+            else:
+                self.gen.backward(self.S, 1.0 / (self.b * self.N))
             self.gen.adam()
 
     def maybe_swap(self, epoch: int) -> Optional[torch.Tensor]:
@@ -241,6 +254,8 @@ class MDGANEngine:
     # ------------------------------------------------------------------------------------------ results
     def mean_d_loss(self) -> List[float]:
         """worker.py:215 -- per hosted worker, mean over the local epochs (synchronises)."""
+        if self.peer:
+            self.exchange.check()
         return self.d_loss[:, : self.cfg.local_epochs].mean(dim=1).tolist()
 
     def swap_partner(self, n: int) -> Optional[int]:

@@ -26,6 +26,8 @@ from . import routing
 
 
 class Exchange:
+    mode = "nccl"   # how C3 / C4 travel: torch.distributed collectives (NCCL on GPUs, gloo in the CPU protocol tests)
+
     def __init__(self, proc: int, n_procs: int, n_workers: int):
         self.proc, self.n_procs, self.n_workers = proc, n_procs, n_workers
         if n_procs > 1 and not dist.is_initialized():
@@ -99,3 +101,120 @@ class Exchange:
                 f32.copy_(rf)
                 i64.copy_(ri)
         return changed
+
+
+class PeerExchange(Exchange):
+    """C4 and C3 over peer-mapped memory (NVLink / NVSwitch) instead of collectives; C5 / C6 as in `Exchange`.
+
+    Every process allocates the same three buffers in torch symmetric memory (peer-mapped at rendezvous):
+      X     [k*b, C, H, W]   its copy of the generated batches; process 0 PUSHES X into all copies with one kernel of
+                             plain stores to the peers' addresses (mdgan_peer_push);
+      F     [N, b, C, H, W]  feedback slices, used on process 0 only: worker n's last data-gradient kernel stores
+                             dBCE/dX_g STRAIGHT into process 0's F[n] over NVLink (no staging, no reduce); the generator's
+                             tanh backward sums the slices of each generated batch in ascending worker order
+                             (mdgan_tanh_backward_slices), which is bit-identical to the single-process accumulation;
+      flags [64] int32       epoch flags: [0] "X is there" (written by process 0 into every peer), [p] "process p's
+                             feedback is there" (written by p into process 0).  Release / acquire at system scope.
+    Per iteration a process launches two tiny flag kernels instead of two collectives, and the whole iteration --
+    exchange included -- is graph-capturable with no communicator inside the graph.
+    Ordering argument (no further synchronisation is needed): process 0 overwrites the peers' X for iteration i+1 only
+    after it consumed every F flag of iteration i, which each worker raises after its last read of X(i); a worker
+    overwrites F[n] for iteration i+1 only after it saw X(i+1), which process 0 produces after reading F(i)."""
+
+    mode = "peer"
+
+    def __init__(self, proc: int, n_procs: int, n_workers: int, device: torch.device, k: int, b: int, image_shape):
+        super().__init__(proc, n_procs, n_workers)
+        import torch.distributed._symmetric_memory as symm
+
+        if n_procs > 63:
+            raise RuntimeError("PeerExchange: at most 63 processes (one flag word each)")
+        group = dist.group.WORLD.group_name
+        f = dict(dtype=torch.float32, device=device)
+        self.X = symm.empty((k * b, *image_shape), **f)
+        self.F = symm.empty((n_workers, b, *image_shape), **f)
+        self.flags = symm.empty((64,), dtype=torch.int32, device=device)
+        hx, hf, hg = (symm.rendezvous(t, group) for t in (self.X, self.F, self.flags))
+        self.X.zero_()
+        self.F.zero_()
+        self.flags.zero_()
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.F_root = self.F if proc == 0 else hf.get_buffer(0, tuple(self.F.shape), torch.float32)
+        self._handles = (hx, hf, hg)
+        if proc == 0:
+            self.x_addrs = torch.tensor([int(p) for p in hx.buffer_ptrs], dtype=torch.int64).to(device)
+            self.sig_addrs = torch.tensor([int(hg.buffer_ptrs[p]) for p in range(1, n_procs)] or [0],
+                                          dtype=torch.int64).to(device)
+            self.wait_flags, self.n_wait, self.n_sig = self.flags[1:n_procs], n_procs - 1, n_procs - 1
+        else:
+            self.x_addrs = None
+            self.sig_addrs = torch.tensor([int(hg.buffer_ptrs[0]) + 4 * proc], dtype=torch.int64).to(device)
+            self.wait_flags, self.n_wait, self.n_sig = self.flags[0:1], 1, 1
+        torch.cuda.synchronize(device)
+        dist.barrier()  # nobody raises a flag before every process has cleared its own
+
+    def feedback_slice(self, n: int) -> torch.Tensor:
+        """Where worker n's feedback goes: process 0's F[n] (a peer-mapped tensor on the other processes)."""
+        return self.F_root[n]
+
+    # ---- C4: process 0 pushes X into every copy and raises the peers' flag; the others wait for it
+    def broadcast_fakes(self, X: torch.Tensor) -> None:
+        from . import ops
+
+        if self.proc == 0:
+            ops.peer_push(X, self.x_addrs, self.n_procs)
+            if self.n_sig:
+                ops.peer_signal(self.sig_addrs, self.n_sig, self.epoch, advance=False)
+        else:
+            ops.peer_wait(self.wait_flags, self.n_wait, self.epoch, False, self.err)
+
+    # ---- C3: the feedback is already in process 0's memory; only the flags move
+    def reduce_feedback(self, S: Optional[torch.Tensor] = None) -> None:
+        from . import ops
+
+        if self.proc == 0:
+            ops.peer_wait(self.wait_flags, self.n_wait, self.epoch, True, self.err)
+        else:
+            ops.peer_signal(self.sig_addrs, self.n_sig, self.epoch, advance=True)
+
+    def check(self) -> None:
+        """Raise if a flag wait timed out (call at a point that synchronises anyway)."""
+        if int(self.err.item()) != 0:
+            raise RuntimeError("peer exchange: a flag did not arrive within the time-out (a peer process died?)")
+
+
+def make_exchange(proc: int, n_procs: int, n_workers: int, device: torch.device, k: int, b: int, image_shape) -> Exchange:
+    """MDGAN_EXCHANGE = peer | nccl | auto (default).  auto: peer-memory exchange when every process can set it up,
+    otherwise NCCL collectives (announced on stderr; both are device paths, there is no host fallback)."""
+    import os
+    import sys
+
+    want = os.environ.get("MDGAN_EXCHANGE", "auto").lower()
+    if n_procs == 1 or device.type != "cuda" or want == "nccl":
+        return Exchange(proc, n_procs, n_workers)
+    ex, why = None, ""
+    vote_group = _ctl_group()  # collective: created by every process before anything can fail
+    try:
+        ex = PeerExchange(proc, n_procs, n_workers, device, k, b, image_shape)
+    except Exception as e:  # noqa: BLE001 -- any set-up failure means "no peer memory here"
+        why = repr(e)
+    ok = torch.tensor([1 if ex is not None else 0])
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=vote_group)
+    if int(ok.item()) == 1:
+        return ex
+    if want == "peer":
+        raise RuntimeError(f"MDGAN_EXCHANGE=peer but the peer-memory exchange could not be set up: {why or 'on another process'}")
+    print(f"[mdgan_b200] process {proc}: peer-memory exchange unavailable ({why or 'another process failed'}); "
+          "using NCCL collectives", file=sys.stderr, flush=True)
+    return Exchange(proc, n_procs, n_workers)
+
+
+_CTL = None
+
+
+def _ctl_group():
+    global _CTL
+    if _CTL is None:
+        _CTL = dist.new_group(backend="gloo")
+    return _CTL

@@ -366,11 +366,17 @@ class GenNet:
         ops.thin_up(self.a[-1], P[last.weight], self.X, act_tanh=True)
         return self.X
 
-    def backward(self, s: torch.Tensor, scale: float) -> None:
-        """s NCHW [n, C, H, W]: per-sample sum of the feedbacks routed to that sample; grads = scale * J^T s."""
+    def backward(self, s: Optional[torch.Tensor], scale: float, slices=None) -> None:
+        """s NCHW [n, C, H, W]: per-sample sum of the feedbacks routed to that sample; grads = scale * J^T s.
+        slices = (F [N, b, C, H, W], k, N) instead of s: the per-worker feedbacks, summed per generated batch inside
+        the tanh-backward kernel (peer-memory exchange)."""
         n, P, Gd, L = self.n, self.state.p, self.state.g, self.L
         last = L[-1]
-        ops.tanh_backward(s, self.X, self.dXt, scale)
+        if slices is not None:
+            F_, k_, N_ = slices
+            ops.tanh_backward_slices(F_, self.X, self.dXt, k_, N_, scale)
+        else:
+            ops.tanh_backward(s, self.X, self.dXt, scale)
         with ops.side_branch():  # weight gradients run next to the data-gradient chain (ops.side_branch)
             ops.thin_wgrad(self.a[-1], self.dXt, self.partial[-1], Gd[last.weight])
         ops.thin_down(self.dXt, P[last.weight], self.da[-1], act=ops.ACT_NONE)

@@ -350,6 +350,30 @@ def tanh_backward(s, x, out, scale: float):
     return out
 
 
+def tanh_backward_slices(F, x, out, k: int, N: int, scale: float):
+    """F [N, b*C*H*W] feedback slices (worker order), x / out [k*b, C, H, W]: group sum per generated batch + tanh'."""
+    n_per = x.numel() // k
+    _run("tanh_backward", 1, 0, 4.0 * (F.numel() + 2 * x.numel()),
+         lambda: _lib.load().mdgan_tanh_backward_slices(_ptr(F), _ptr(x), _ptr(out), n_per, k, N, scale, _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- peer-memory exchange (NVLink)
+def peer_signal(flag_addrs: torch.Tensor, n: int, epoch: torch.Tensor, advance: bool):
+    _run("peer_signal", 1, 0, 4.0 * n,
+         lambda: _lib.load().mdgan_peer_signal(_ptr(flag_addrs), n, _ptr(epoch), int(advance), _stream()))
+
+
+def peer_wait(flags: torch.Tensor, n: int, epoch: torch.Tensor, advance: bool, err: torch.Tensor):
+    _run("peer_wait", 1, 0, 4.0 * n,
+         lambda: _lib.load().mdgan_peer_wait(_ptr(flags), n, _ptr(epoch), int(advance), _ptr(err), _stream()))
+
+
+def peer_push(src: torch.Tensor, dst_addrs: torch.Tensor, n_dst: int):
+    _run("peer_push", 1, 0, 4.0 * src.numel() * (1 + n_dst),
+         lambda: _lib.load().mdgan_peer_push(_ptr(src), _ptr(dst_addrs), n_dst, src.numel(), _stream()))
+
+
 # ----------------------------------------------------------------------------- head / loss / optimiser
 def head_pack(w, wt):
     """w PyTorch [1, C, k, k] -> wt [k*k, C] (the NHWC order of the activations)."""

@@ -157,6 +157,25 @@ int mdgan_pad_rows(const float* in, float* out, int rows, int cols_in, int cols_
  * (actors/server.py:271-297, collapsed by linearity of the VJP). */
 int mdgan_sum_slices(const float* in, float* out, long long n, int count, long long stride, void* stream);
 
+/* ---- peer-memory exchange over NVLink / NVSwitch (one process per GPU; buffers allocated in peer-mapped
+ * "symmetric" memory, e.g. torch.distributed._symmetric_memory) ---------------------------------------------------
+ * Replaces the per-iteration messages of the reference: generated batches server.py:238-246 / worker.py:181-182,
+ * error feedback worker.py:232-233 / server.py:234, and the sum over workers server.py:266-302.  All four are ordinary
+ * stream-ordered kernels (capturable in a CUDA graph); no collective library call is involved.
+ *   mdgan_peer_signal: *(int*)flag_addrs_dev[i] = *epoch + 1 for i < n (peer-mapped addresses, release at system
+ *     scope after a system fence); advance = 1 also stores *epoch + 1 to *epoch.
+ *   mdgan_peer_wait  : spins until flags[i] >= *epoch + 1 for i < n (local memory written by peers, acquire at
+ *     system scope); advance as above; *err = 1 if a flag does not arrive within ~30 s (the wait is then abandoned).
+ *   mdgan_peer_push  : dst_j[0..n) = src[0..n) for the n_dst peer-mapped destinations dst_addrs_dev[j] (n % 4 == 0).
+ *   mdgan_tanh_backward_slices: out[s][j] = scale * (1 - x[s][j]^2) * sum_{w = s, s+k, .. < N} F[w][j], j < n_per_slot:
+ *     the feedbacks of the workers sharing generated batch s, summed in ascending worker order, fused with the
+ *     generator's tanh backward (F: [N][n_per_slot] slices written by the workers' feedback kernels). */
+int mdgan_peer_signal(const unsigned long long* flag_addrs_dev, int n, int* epoch, int advance, void* stream);
+int mdgan_peer_wait(const int* flags, int n, int* epoch, int advance, int* err, void* stream);
+int mdgan_peer_push(const float* src, const unsigned long long* dst_addrs_dev, int n_dst, long long n, void* stream);
+int mdgan_tanh_backward_slices(const float* F, const float* x, float* out, long long n_per_slot, int k, int N,
+                               float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
