@@ -364,28 +364,47 @@ def run_ours(args) -> None:
         if rep == 0:
             engine.device_iteration()  # eager warm-up after the graph replays
             continue
+        # Hold the stream with a spin kernel (~10 ms) while the host queues the whole iteration + its events, so the
+        # event intervals measure device execution back to back, not the host's per-launch latency.
+        torch.cuda._sleep(20_000_000)
         ops.set_observer(timer)
         engine.device_iteration()
         ops.set_observer(None)
+        torch.cuda.synchronize(dev)
     per_op = timer.summary()
     peaks = load_peaks()
     total_ms = sum(a["ms"] for a in per_op.values()) or 1.0
     top = max(per_op, key=lambda n: per_op[n]["ms"])
     a = per_op[top]
     tensor_bound = top in ("conv_down", "conv_up", "conv_dense", "wgrad_gemm")
+    traffic, traffic_note = None, None
+    tpath = REPO / "profiles" / "r01_traffic.json"
+    if tpath.exists() and args.dataset == "MNIST_DCGAN" and b == 64:
+        kname = "void wgrad_gemm_kernel" if top == "wgrad_gemm" else ("void conv_gemm_kernel" if tensor_bound else None)
+        rec = json.loads(tpath.read_text()).get("MNIST_DCGAN_b64", {}).get(kname)
+        if rec:
+            traffic = rec["dram_bytes_per_launch_avg"]
+            traffic_note = ("ncu --set full capture of this workload (profiles/r01_traffic.json), cold caches, average "
+                            "over the launches of the kernel")
     if tensor_bound:
         achieved = a["flops"] / (a["ms"] * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        x3 = args.precision == "tf32x3"
+        ceiling = peak / (6.0 if x3 else 2.0)
         roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic,
+                    "mode_ceiling": ceiling, "frac_of_mode_ceiling": achieved / ceiling,
                     "peak_note": f"{peaks['source']} dense bf16 cuBLAS (sustained) from MEASURED_PEAKS.json; kind::tf32 "
                                  "runs at half that rate and the tf32x3 parity mode issues 3 MMAs per algorithmic MAC "
-                                 "(ceiling = peak/6)"}
+                                 "(mode_ceiling = peak/6 for tf32x3, peak/2 for tf32); achieved counts ALGORITHMIC "
+                                 "FLOPs (2*M*N*K of the layer), not the three tensor-core passes"}
     else:
         achieved = a["bytes"] / (a["ms"] * 1e-3) / 1e9
         peak = peaks["hbm_gbs"]
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_note": f"{peaks['source']} HBM copy bandwidth"}
+                    "frac": achieved / peak, "traffic": traffic, "peak_note": f"{peaks['source']} HBM copy bandwidth"}
+    if traffic_note:
+        roofline["traffic_note"] = traffic_note
     roofline["avg_launch_us"] = a["ms"] * 1e3 / max(a["calls"], 1)
     roofline["launches_timed"] = a["calls"]
     roofline["share_of_step"] = a["ms"] / total_ms

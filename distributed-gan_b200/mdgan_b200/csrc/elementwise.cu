@@ -55,8 +55,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, float* __restri
 // int64 words in device memory: {W ptr, out ptr, mode, N, C, N_pad, C_pad, KK, total elements, first block, split}.
 // mode 0..2 as above; mode 3 is the discriminator head re-order wt[hw*C + c] = w[c*HW + hw] (N = HW, no TF32 rounding:
 // the head runs in fp32 on CUDA cores).
+// Modes 0 / 1 (the 4x4 stencils, > 95 % of the bytes) are tiled: a block owns one output row n and 32 channels, reads
+// the 32 x 16 source taps as 64-byte runs, transposes them through shared memory and writes sixteen 128-byte runs
+// (job blocks = N_pad * C_pad / 32); modes 2 / 3 go element-wise (job blocks = ceil(total / 256)).
 constexpr int kPackJobWords = 11;
-__global__ void pack_weights_multi_kernel(const long long* __restrict__ jobs, int n_jobs) {
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const long long* __restrict__ jobs, int n_jobs) {
+  __shared__ float tile[16][33];
   pdl_enter();
   int j = 0;
   while (j + 1 < n_jobs && (long long)blockIdx.x >= jobs[(j + 1) * kPackJobWords + 9]) ++j;
@@ -66,36 +70,56 @@ __global__ void pack_weights_multi_kernel(const long long* __restrict__ jobs, in
   const int mode = (int)jb[2], N = (int)jb[3], C = (int)jb[4], N_pad = (int)jb[5], C_pad = (int)jb[6], KK = (int)jb[7];
   const long long total = jb[8];
   const int split = (int)jb[10];
-  const long long idx = ((long long)blockIdx.x - jb[9]) * blockDim.x + threadIdx.x;
+  const long long blk = (long long)blockIdx.x - jb[9];
+  if (mode <= 1) {
+    const int chunks = C_pad >> 5;
+    const int n = blk / chunks, c0 = (int)(blk - (long long)n * chunks) << 5;
+    // source: mode 0 W[n][c][16], mode 1 W[c][n][16]; element e = cl * 16 + k of the 32 x 16 tile
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int e = threadIdx.x + 256 * r;
+      const int cl = e >> 4, k = e & 15, c = c0 + cl;
+      float v = 0.f;
+      if (n < N && c < C) v = mode == 0 ? W[((long long)n * C + c) * 16 + k] : W[((long long)c * N + n) * 16 + k];
+      tile[k][cl] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int e = threadIdx.x + 256 * r;
+      const int row = e >> 5, cl = e & 31;  // row: mode 0 the tap; mode 1 (ph, t) = (row >> 2, row & 3)
+      float v;
+      long long idx;
+      if (mode == 0) {
+        v = tile[row][cl];
+        idx = ((long long)n * 16 + row) * C_pad + c0 + cl;
+      } else {
+        const int ph = row >> 2, t = row & 3;
+        const int kh = (1 - (ph >> 1)) + 2 * (t >> 1), kw = (1 - (ph & 1)) + 2 * (t & 1);
+        v = tile[kh * 4 + kw][cl];
+        idx = (((long long)ph * N_pad + n) * 4 + t) * C_pad + c0 + cl;
+      }
+      const float hi = to_tf32(v);
+      out[idx] = hi;
+      if (split) out[total + idx] = to_tf32(v - hi);
+    }
+    return;
+  }
+  const long long idx = blk * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  float v = 0.f;
-  if (mode == 0) {
-    const int c = idx % C_pad;
-    const int tap = (idx / C_pad) % 16;
-    const int n = idx / (16LL * C_pad);
-    if (n < N && c < C) v = W[((long long)n * C + c) * 16 + tap];
-  } else if (mode == 1) {
-    const int c = idx % C_pad;
-    const int t = (idx / C_pad) % 4;
-    const int n = (idx / (4LL * C_pad)) % N_pad;
-    const int ph = idx / (4LL * C_pad * N_pad);
-    const int kh = (1 - (ph >> 1)) + 2 * (t >> 1);
-    const int kw = (1 - (ph & 1)) + 2 * (t & 1);
-    if (n < N && c < C) v = W[((long long)c * N + n) * 16 + kh * 4 + kw];
-  } else if (mode == 2) {
+  if (mode == 2) {
     const int c = idx % C_pad;
     const long long row = idx / C_pad;
     const int n = row % N;
     const int kk = row / N;
-    if (c < C) v = W[((long long)c * N + n) * KK + kk];
+    const float v = c < C ? W[((long long)c * N + n) * KK + kk] : 0.f;
+    const float hi = to_tf32(v);
+    out[idx] = hi;
+    if (split) out[total + idx] = to_tf32(v - hi);
   } else {
     const int hw = idx / C, c = idx - (long long)hw * C;
     out[idx] = W[(long long)c * N + hw];
-    return;
   }
-  const float hi = to_tf32(v);
-  out[idx] = hi;
-  if (split) out[total + idx] = to_tf32(v - hi);
 }
 
 // Reduce split-K partial slices and scatter to the PyTorch parameter layout.

@@ -105,6 +105,26 @@ class FlatState:
             off += k
         self.step[0:1].fill_(step)
 
+    def state_dict_from(self, host_f32: torch.Tensor, host_i64: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """The module's `state_dict()` (key order preserved) rebuilt from host copies of the two flat buffers -- used
+        by the asynchronous checkpoint writer (node._SnapshotWriter)."""
+        out: Dict[str, torch.Tensor] = {}
+        off = 0
+        for n in self.param_names:
+            k = 1
+            for d in self.param_shapes[n]:
+                k *= d
+            out[n] = host_f32[off: off + k].view(self.param_shapes[n]).clone()
+            off += k
+        for n in self.fbuf_names:
+            shape = tuple(self.b[n].shape)
+            k = self.b[n].numel()
+            out[n] = host_f32[off: off + k].view(shape).clone()
+            off += k
+        for i, n in enumerate(self.ibuf_names):
+            out[n] = host_i64[i].clone()
+        return {n: out[n] for n in self.key_order}
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Host copy in the module's own `state_dict()` key order (what torch.save of the reference writes)."""
         return {n: (self.p[n] if n in self.p else self.b[n]).detach().cpu().clone() for n in self.key_order}

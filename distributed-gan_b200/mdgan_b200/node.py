@@ -13,6 +13,8 @@ from __future__ import annotations
 import csv
 import logging
 import os
+import queue
+import threading
 import time
 from datetime import timedelta
 from pathlib import Path
@@ -99,6 +101,79 @@ def _save_grid(images: torch.Tensor, path: Path, normalize: bool) -> None:
     to_pil_image(grid).save(path)
 
 
+class _SnapshotWriter:
+    """The reference's periodic side outputs (image grid + generator checkpoint, server.py:336-367) without stalling
+    the training loop: the generated batch and the generator's flat state are cloned on the
+    compute stream (device-to-device, microseconds, so the next Adam step cannot touch the snapshot), copied to pinned
+    host memory on a side stream, and a background thread writes the PNG / .pt once the copy event has fired."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.side = torch.cuda.Stream(device=device)
+        self.q: "queue.Queue" = queue.Queue()
+        self.error: Optional[BaseException] = None
+        self.slots = []          # (pinned x, pinned f32, pinned i64, free-flag) ring of two
+        self.thread = threading.Thread(target=self._run, name="mdgan-snapshot-writer", daemon=True)
+        self.thread.start()
+
+    def _slot(self, x, f32, i64):
+        for s in self.slots:
+            if s[3].is_set():
+                s[3].clear()
+                return s
+        if len(self.slots) >= 2:       # both in flight: wait for the older one (the loop is producing faster than disk)
+            s = self.slots[0]
+            s[3].wait()
+            s[3].clear()
+            self.slots.append(self.slots.pop(0))
+            return s
+        s = (torch.empty(x.shape, dtype=x.dtype, pin_memory=True), torch.empty(f32.shape, dtype=f32.dtype, pin_memory=True),
+             torch.empty(i64.shape, dtype=i64.dtype, pin_memory=True), threading.Event())
+        self.slots.append(s)
+        return s
+
+    def submit(self, engine: MDGANEngine, image_path: Path, weights_path: Path) -> None:
+        main = torch.cuda.current_stream(self.device)
+        st = engine.gen.state
+        x, f32, i64 = engine.X.detach().clone(), st.state_f32.clone(), st.state_i64.clone()
+        hx, hf, hi, free = self._slot(x, f32, i64)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            hx.copy_(x, non_blocking=True)
+            hf.copy_(f32, non_blocking=True)
+            hi.copy_(i64, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        for t in (x, f32, i64):
+            t.record_stream(self.side)
+        self.q.put((done, hx, hf, hi, free, st, image_path, weights_path))
+
+    def _run(self) -> None:
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            done, hx, hf, hi, free, st, image_path, weights_path = item
+            try:
+                done.synchronize()
+                fake = hx.clone()
+                sd = st.state_dict_from(hf, hi)
+                free.set()
+                fake = fake.repeat(1, 3, 1, 1) if fake.shape[1] < 3 else fake
+                _save_grid((fake + 1) * 0.5, image_path, normalize=False)
+                weights_path.parent.mkdir(parents=True, exist_ok=True)
+                torch.save(sd, weights_path)
+            except BaseException as e:  # noqa: BLE001 -- surfaced by close()
+                self.error = e
+                free.set()
+
+    def close(self) -> None:
+        self.q.put(None)
+        self.thread.join()
+        if self.error is not None:
+            raise RuntimeError("snapshot writer failed") from self.error
+
+
 def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: torch.device, cfg: EngineConfig,
              generator: Optional[nn.Module], discriminators: Dict[int, nn.Module], dataset, get_subset=None,
              epochs: int, log_interval: int, log_folder: Path, dataset_name: str, iid: bool = True, n_samples: int = 5,
@@ -169,6 +244,7 @@ def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: 
     # MDGAN_SYNC_TIMING=1 (per-phase device-synchronised CSV spans) keep the eager phase-by-phase launches.
     use_graph = os.environ.get("MDGAN_GRAPH", "1") == "1" and not sync_timing
     FID, IS = _maybe_metrics()
+    snapshots = _SnapshotWriter(device) if (proc == 0 and FID is None) else None
     for epoch in range(epochs):
         if use_graph and epoch == 2:
             engine.capture()
@@ -222,7 +298,9 @@ def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: 
             wrows[n]["mean_d_loss"] = losses[i]
             worker_writers[n].writerow(wrows[n])
         if proc == 0:
-            if epoch % log_interval == 0 or epoch == epochs - 1:  # server.py:336-367
+            if (epoch % log_interval == 0 or epoch == epochs - 1) and snapshots is not None:  # server.py:336-367
+                snapshots.submit(engine, image_dir / f"generated_epoch_{epoch}.png", weights_dir / f"generator_{epoch}.pt")
+            elif epoch % log_interval == 0 or epoch == epochs - 1:  # with torchmetrics: FID / IS need the images now
                 fake = engine.X.detach().cpu()
                 fake = fake.repeat(1, 3, 1, 1) if fake.shape[1] < 3 else fake
                 fake = (fake + 1) * 0.5
@@ -246,6 +324,8 @@ def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: 
             server_w.writerow(srow)
 
     torch.cuda.synchronize(device)
+    if snapshots is not None:
+        snapshots.close()
     engine.sync_modules()
     engine.close()
     if proc == 0:

@@ -184,7 +184,8 @@ class PackPlan:
         _ptr(W), _ptr(out)  # CUDA + contiguous checks
         self.jobs.append([W.data_ptr(), out.data_ptr(), mode, N, Cc, Np, Cp, KK, total, self.blocks, split])
         self.keep += [W, out]
-        self.blocks += (total + 255) // 256
+        # modes 0 / 1 are tiled (one block per output row and 32 channels), the others element-wise
+        self.blocks += (Np * (Cp // 32)) if mode <= 1 else (total + 255) // 256
         self.nbytes += 4.0 * (W.numel() + out.numel())
 
     def add_down(self, W, out):
