@@ -23,6 +23,8 @@
 //            accuracy (the parity mode: plain TF32 through BatchNorm + (Leaky)ReLU gates is only good to a few
 //            percent on gradients, exactly like cuDNN's TF32 path -- see DESIGN.md).  The A producers split their
 //            own cp.async'd chunks in shared memory; the weight pack kernel pre-splits B.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -85,6 +87,94 @@ __device__ __forceinline__ float round_to_tf32(float x) {
 
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Epilogue of one 128 x BN tile: warp (q = TMEM lane quarter, half = column half) reads its 32 rows x BN/2 columns of
+// the kAccs accumulators (summed with round-to-nearest fp32 adds), applies bias / tanh / TF32 rounding / the fused
+// activation-backward gate and stores NHWC (float4) or scatters NCHW (optionally accumulating).
+template <int BN, int kAccs>
+__device__ __forceinline__ void conv_epilogue(const ConvGemmParams& p, uint32_t tmem_base, int q, int half, int lane,
+                                              int m0, int n0, int ph, int pw) {
+  constexpr int kColsPerHalf = (BN >= 32) ? BN / 2 : BN;
+  if (BN >= 32 || half == 0) {
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool ok = m < p.M;
+    const int mm = ok ? m : 0;
+    const int img = mm / (p.Hg * p.Wg);
+    const int rem = mm - img * (p.Hg * p.Wg);
+    const int gi = rem / p.Wg, gj = rem - gi * p.Wg;
+    int Ho, Wo, oh, ow;
+    if (p.mode == 1) { Ho = 2 * p.Hg; Wo = 2 * p.Wg; oh = 2 * gi + ph; ow = 2 * gj + pw; }
+    else { Ho = p.Hg; Wo = p.Wg; oh = gi; ow = gj; }
+#pragma unroll 1
+    for (int c16 = 0; c16 < kColsPerHalf; c16 += 16) {
+      const int col = half * kColsPerHalf + c16;
+      float v[16];
+      tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
+      if (kAccs > 1) {
+        float t[16];
+#pragma unroll
+        for (int a = 1; a < kAccs; ++a) {
+          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col, t);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += t[j];
+        }
+      }
+        if (!ok) continue;
+        const int nbase = n0 + col;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = v[j];
+          if (p.bias != nullptr && nbase + j < p.N) x += __ldg(p.bias + nbase + j);
+          if (p.act == 1) x = tanhf(x);
+          if (p.round_tf32) x = round_to_tf32(x);
+          v[j] = x;
+        }
+        if (!p.out_nchw) {
+          const size_t oidx = (static_cast<size_t>((img * Ho + oh) * Wo + ow)) * p.N + nbase;
+          float* o = p.dst + oidx;
+          if (nbase + 16 <= p.N && (p.N & 3) == 0) {
+            if (p.gate != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p.gate + oidx + j));
+                const float neg = p.gate_act == 2 ? p.gate_slope : 0.f;
+                v[j] *= a.x > 0.f ? 1.f : neg;
+                v[j + 1] *= a.y > 0.f ? 1.f : neg;
+                v[j + 2] *= a.z > 0.f ? 1.f : neg;
+                v[j + 3] *= a.w > 0.f ? 1.f : neg;
+                if (p.round_tf32) {
+                  v[j] = round_to_tf32(v[j]); v[j + 1] = round_to_tf32(v[j + 1]);
+                  v[j + 2] = round_to_tf32(v[j + 2]); v[j + 3] = round_to_tf32(v[j + 3]);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nbase + j < p.N) {
+                float x = v[j];
+                if (p.gate != nullptr) {
+                  x *= __ldg(p.gate + oidx + j) > 0.f ? 1.f : (p.gate_act == 2 ? p.gate_slope : 0.f);
+                  if (p.round_tf32) x = round_to_tf32(x);
+                }
+                o[j] = x;
+              }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nbase + j < p.N) {
+              float* o = p.dst + (static_cast<size_t>(img * p.N + nbase + j) * Ho + oh) * Wo + ow;
+              *o = p.accumulate ? (*o + v[j]) : v[j];
+            }
+        }
+      }
+    }
 }
 
 template <int BN, int STAGES, bool X3>
@@ -202,88 +292,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
     // ------------------------------------------------------------------ epilogue
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after_sync();
-    const int q = warp & 3;
-    constexpr int kColsPerHalf = (BN >= 32) ? BN / 2 : BN;
-    const int half = warp >> 2;
-    if (BN >= 32 || half == 0) {
-      const int row = q * 32 + lane;
-      const int m = m0 + row;
-      const bool ok = m < p.M;
-      const int mm = ok ? m : 0;
-      const int img = mm / (p.Hg * p.Wg);
-      const int rem = mm - img * (p.Hg * p.Wg);
-      const int gi = rem / p.Wg, gj = rem - gi * p.Wg;
-      int Ho, Wo, oh, ow;
-      if (p.mode == 1) { Ho = 2 * p.Hg; Wo = 2 * p.Wg; oh = 2 * gi + ph; ow = 2 * gj + pw; }
-      else { Ho = p.Hg; Wo = p.Wg; oh = gi; ow = gj; }
-#pragma unroll 1
-      for (int c16 = 0; c16 < kColsPerHalf; c16 += 16) {
-        const int col = half * kColsPerHalf + c16;
-        float v[16];
-        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
-        if (X3) {
-          float t[16];
-#pragma unroll
-          for (int a = 1; a < S::kAccs; ++a) {
-            tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col, t);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += t[j];
-          }
-        }
-        if (!ok) continue;
-        const int nbase = n0 + col;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = v[j];
-          if (p.bias != nullptr && nbase + j < p.N) x += __ldg(p.bias + nbase + j);
-          if (p.act == 1) x = tanhf(x);
-          if (p.round_tf32) x = round_to_tf32(x);
-          v[j] = x;
-        }
-        if (!p.out_nchw) {
-          const size_t oidx = (static_cast<size_t>((img * Ho + oh) * Wo + ow)) * p.N + nbase;
-          float* o = p.dst + oidx;
-          if (nbase + 16 <= p.N && (p.N & 3) == 0) {
-            if (p.gate != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(p.gate + oidx + j));
-                const float neg = p.gate_act == 2 ? p.gate_slope : 0.f;
-                v[j] *= a.x > 0.f ? 1.f : neg;
-                v[j + 1] *= a.y > 0.f ? 1.f : neg;
-                v[j + 2] *= a.z > 0.f ? 1.f : neg;
-                v[j + 3] *= a.w > 0.f ? 1.f : neg;
-                if (p.round_tf32) {
-                  v[j] = round_to_tf32(v[j]); v[j + 1] = round_to_tf32(v[j + 1]);
-                  v[j + 2] = round_to_tf32(v[j + 2]); v[j + 3] = round_to_tf32(v[j + 3]);
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (nbase + j < p.N) {
-                float x = v[j];
-                if (p.gate != nullptr) {
-                  x *= __ldg(p.gate + oidx + j) > 0.f ? 1.f : (p.gate_act == 2 ? p.gate_slope : 0.f);
-                  if (p.round_tf32) x = round_to_tf32(x);
-                }
-                o[j] = x;
-              }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nbase + j < p.N) {
-              float* o = p.dst + (static_cast<size_t>(img * p.N + nbase + j) * Ho + oh) * Wo + ow;
-              *o = p.accumulate ? (*o + v[j]) : v[j];
-            }
-        }
-      }
-    }
+    conv_epilogue<BN, X3 ? S::kAccs : 1>(p, tmem_base, warp & 3, warp >> 2, lane, m0, n0, ph, pw);
     tc_fence_before_sync();
   } else if (warp == 8) {
     // ------------------------------------------------------------------ B producer (TMA)
@@ -341,6 +350,260 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
     tc_fence_after_sync();
     tmem_dealloc<S::kTmemCols>(tmem_base);
   }
+}
+
+// ================================================================================================================
+// tf32x3 variant with the ACTIVATION operand in tensor memory.  The shared-memory port bounds the kernel above (per K
+// step: 96 KB of MMA operand reads + 32 KB of producer stores + 32 KB of TMA writes against 768 clk of MMA time,
+// profiles/r01_ncu_full_conv_wgrad.md).  Here the activations cross shared memory once, as raw fp32 (16 KB stored,
+// 16 KB read back row-wise), are split into TF32 hi / lo in registers by four "transposer" warps that own one TMEM lane
+// quarter each, and land in TMEM (tcgen05.st) where the twelve MMAs of the K step read them for free; only the weights
+// (TMA) stay on the port: 16 + 16 + 32 + 48 = 112 KB per K step instead of 160 KB.
+//   warps 0-3  : transposers: raw stage (row-wise, swizzle-aware LDS) -> hi/lo -> TMEM A stage
+//   warps 4-11 : loaders (global -> registers kPrefetch K steps ahead -> raw fp32 stage), then the epilogue
+//   warp  12   : B producer (TMA, hi + lo)        warp 13: TMEM allocator + single-thread MMA issuer
+constexpr int kTaThreads = (4 + kNumProducerWarps + 2) * 32;
+
+template <int BN>
+struct ConvTaSmem {
+  static constexpr int kRawBytes = kBM * 128;
+  static constexpr int kRawStages = 4;
+  static constexpr int kBBytes = BN * 128;              // one of hi / lo
+  static constexpr int kBStageBytes = 2 * kBBytes;      // [B_hi | B_lo]
+  static constexpr int kBStages = BN > 64 ? 3 : 4;
+  static constexpr int kAStages = BN > 64 ? 2 : 3;      // TMEM stages of [A_hi (32 columns) | A_lo (32 columns)]
+  static constexpr int kBOff = kRawStages * kRawBytes;
+  static constexpr int kBarOffset = kBOff + kBStages * kBStageBytes;
+  static constexpr int kNumBars = 2 * kRawStages + 2 * kBStages + 2 * kAStages + 1;
+  static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+  static constexpr int kMain = BN > 64 ? 2 : 4;
+  static constexpr int kAccs = kMain + 1;
+  static constexpr int kACol0 = kAccs * BN;
+  static constexpr uint32_t kTmemCols = 512;
+  static_assert(kACol0 + kAStages * 64 <= 512, "TMEM holds 512 columns");
+};
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kTaThreads, 1)
+conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParams p) {
+  using S = ConvTaSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* raw_empty = raw_full + S::kRawStages;
+  uint64_t* b_full = raw_empty + S::kRawStages;
+  uint64_t* b_empty = b_full + S::kBStages;
+  uint64_t* a_full = b_empty + S::kBStages;
+  uint64_t* a_empty = a_full + S::kAStages;
+  uint64_t* tmem_full_bar = a_empty + S::kAStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM;
+  const int n0 = blockIdx.y * BN;
+  const int phase = blockIdx.z;
+  const int ph = phase >> 1, pw = phase & 1;
+  const int taps = (p.mode == 0) ? 16 : (p.mode == 1 ? 4 : 1);
+  const int cchunks = p.C / kBK;
+  const int ksteps = taps * cchunks;
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S::kRawStages; ++s) { mbar_init(&raw_full[s], kNumProducerWarps); mbar_init(&raw_empty[s], 4); }
+    for (int s = 0; s < S::kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < S::kAStages; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 12 && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (warp == 13) tmem_alloc<S::kTmemCols>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ transposers: raw stage -> TMEM A stage
+    const int r = warp * 32 + lane;  // tile row == TMEM lane
+    const uint32_t row_base = smem_u32(smem) + r * 128;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + S::kACol0;
+    int s = 0, t = 0;
+    uint32_t pars = 0, part = 0;
+    for (int it = 0; it < ksteps; ++it) {
+      mbar_wait(&raw_full[s], pars);
+      float x[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = lds128(row_base + s * S::kRawBytes + ((c ^ (r & 7)) << 4));
+        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[s]);   // the row is in registers: the loaders may refill the stage
+      float hi[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) hi[j] = tf32_round_fast(x[j]);
+      mbar_wait(&a_empty[t], part ^ 1);            // the MMAs that read this TMEM stage have completed
+      tc_fence_after_sync();
+      tmem_st_x32(t_lane + t * 64, hi);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] -= hi[j];  // lo = x - hi (exact); the tensor core truncates it to TF32
+      tmem_st_x32(t_lane + t * 64 + 32, x);
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[t]);
+      if (++s == S::kRawStages) { s = 0; pars ^= 1; }
+      if (++t == S::kAStages) { t = 0; part ^= 1; }
+    }
+  } else if (warp < 4 + kNumProducerWarps) {
+    // ------------------------------------------------------------------ loaders (raw fp32 tile), then epilogue
+    const int tid = threadIdx.x - 128;
+    const int chunk = tid & 7;
+    const int row_in = tid >> 3;  // 0..31
+    const int SI = (p.mode == 0) ? 2 : 1;
+    int base_off[4], sh0[4], sw0[4];
+    bool row_ok[4];
+    uint32_t soff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = row_in + 32 * i;
+      const int m = m0 + r;
+      row_ok[i] = m < p.M;
+      const int mm = row_ok[i] ? m : 0;
+      const int img = mm / (p.Hg * p.Wg);
+      const int rem = mm - img * (p.Hg * p.Wg);
+      const int gi = rem / p.Wg, gj = rem - gi * p.Wg;
+      sh0[i] = gi * SI;
+      sw0[i] = gj * SI;
+      base_off[i] = ((img * p.Hs + sh0[i]) * p.Ws + sw0[i]) * p.C + chunk * 4;
+      soff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
+    }
+    const uint32_t raw0 = smem_u32(smem);
+    int tap_l = 0, cc_l = 0;
+    auto issue_loads = [&](float4(&buf)[4]) {
+      int dh, dw;
+      if (p.mode == 0) { dh = (tap_l >> 2) - 1; dw = (tap_l & 3) - 1; }
+      else if (p.mode == 1) { dh = ph - (tap_l >> 1); dw = pw - (tap_l & 1); }
+      else { dh = 0; dw = 0; }
+      const int tap_off = (dh * p.Ws + dw) * p.C + cc_l * kBK;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int sh = sh0[i] + dh, sw = sw0[i] + dw;
+        const bool ok = row_ok[i] && sh >= 0 && sh < p.Hs && sw >= 0 && sw < p.Ws;
+        buf[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.src + base_off[i] + tap_off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (++cc_l == cchunks) { cc_l = 0; ++tap_l; }
+    };
+    float4 buf[kPrefetch][4];
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u)
+      if (u < ksteps) issue_loads(buf[u]);
+    int s = 0;
+    uint32_t par = 0;
+    for (int it0 = 0; it0 < ksteps; it0 += kPrefetch) {
+#pragma unroll
+      for (int u = 0; u < kPrefetch; ++u) {
+        const int it = it0 + u;
+        if (it < ksteps) {
+          mbar_wait(&raw_empty[s], par ^ 1);
+          const uint32_t stage = raw0 + s * S::kRawBytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sts128(stage + soff[i], buf[u][i].x, buf[u][i].y, buf[u][i].z, buf[u][i].w);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&raw_full[s]);
+          if (it + kPrefetch < ksteps) issue_loads(buf[u]);
+          if (++s == S::kRawStages) { s = 0; par ^= 1; }
+        }
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after_sync();
+    conv_epilogue<BN, S::kAccs>(p, tmem_base, warp & 3, (warp - 4) >> 2, lane, m0, n0, ph, pw);
+    tc_fence_before_sync();
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------ B producer (TMA, hi + lo)
+    if (lane == 0) {
+      const int row0 = (p.mode == 1 ? phase * p.N_pad : 0) + n0;
+      int s = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < ksteps; ++it) {
+        mbar_wait(&b_empty[s], par ^ 1);
+        mbar_arrive_expect_tx(&b_full[s], S::kBStageBytes);
+        const uint32_t b_dst = smem_u32(smem + S::kBOff + s * S::kBStageBytes);
+        tma_load_2d(b_dst, &tmap_w, &b_full[s], it * kBK, row0);
+        tma_load_2d(b_dst + S::kBBytes, &tmap_w, &b_full[s], it * kBK, row0 + p.lo_row_offset);
+        if (++s == S::kBStages) { s = 0; par ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (A from TMEM, B from shared memory)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem + S::kBOff), 16, 1024);
+      constexpr uint64_t kBStageStep = S::kBStageBytes >> 4, kLoStep = S::kBBytes >> 4;
+      const uint32_t acc_corr = tmem_base + S::kMain * BN;
+      int sb = 0, t = 0;
+      uint32_t parb = 0, part = 0;
+      uint64_t db0 = bdesc0;
+      for (int it = 0; it < ksteps; ++it) {
+        mbar_wait(&a_full[t], part);
+        mbar_wait(&b_full[sb], parb);
+        tc_fence_after_sync();
+        const uint32_t acc = it != 0 ? 1u : 0u;
+        const uint32_t a_hi0 = tmem_base + S::kACol0 + t * 64;
+#pragma unroll
+        for (int k = 0; k < kBK / 8; ++k) {
+          const uint32_t a_hi = a_hi0 + 8 * k, a_lo = a_hi + 32;
+          const uint64_t db = db0 + 2 * k;
+          umma_tf32_ts(acc_corr, a_lo, db, idesc, k == 0 ? acc : 1u);
+          umma_tf32_ts(acc_corr, a_hi, db + kLoStep, idesc, 1u);
+          umma_tf32_ts(tmem_base + (k % S::kMain) * BN, a_hi, db, idesc, k < S::kMain ? acc : 1u);
+        }
+        umma_commit(&a_empty[t]);
+        umma_commit(&b_empty[sb]);
+        db0 += kBStageStep;
+        if (++sb == S::kBStages) { sb = 0; parb ^= 1; db0 = bdesc0; }
+        if (++t == S::kAStages) { t = 0; part ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  }
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after_sync();
+    tmem_dealloc<S::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_conv_gemm_ta(const CUtensorMap& tmap, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
+  using S = ConvTaSmem<BN>;
+  static_assert(S::kDynamic <= 227 * 1024, "shared memory per CTA");
+  static bool configured = false;
+  if (!configured) {
+    MDGAN_CUDA(cudaFuncSetAttribute(conv_gemm_ta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
+    configured = true;
+  }
+  MDGAN_LAUNCH((conv_gemm_ta_kernel<BN>), grid, dim3(kTaThreads), S::kDynamic, st, tmap, p);
+  return 0;
+}
+
+// MDGAN_CONV_TA = 1 (default) | 0: activation operand through tensor memory (tf32x3 only; same arithmetic, same bits).
+static bool conv_ta_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MDGAN_CONV_TA");
+    return e ? e[0] != '0' : true;
+  }();
+  return on;
 }
 
 template <int BN, int STAGES, bool X3>
@@ -414,6 +677,15 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   if (rc != 0) return rc;
   dim3 grid(row_tiles, N_pad / bn, phases);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x3 && conv_ta_enabled()) {
+    switch (bn) {
+      case 128: return launch_conv_gemm_ta<128>(tmap, p, grid, st);
+      case 64: return launch_conv_gemm_ta<64>(tmap, p, grid, st);
+      case 32: return launch_conv_gemm_ta<32>(tmap, p, grid, st);
+      case 16: return launch_conv_gemm_ta<16>(tmap, p, grid, st);
+      default: return MDGAN_ERR_UNSUPPORTED;
+    }
+  }
   switch (bn) {
     case 128: return x3 ? launch_conv_gemm<128, 3, true>(tmap, p, grid, st) : launch_conv_gemm<128, 6, false>(tmap, p, grid, st);
     case 64: return x3 ? launch_conv_gemm<64, 4, true>(tmap, p, grid, st) : launch_conv_gemm<64, 6, false>(tmap, p, grid, st);
