@@ -55,6 +55,40 @@ int get_tmap_2d_f32(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_
   return 0;
 }
 
+// NHWC fp32 activation tensor [n_img][Hs][Ws][C] -> 4-D tensor map whose box is one 128-row im2col tile of a single
+// tap and 32-channel chunk: {32 channels, bw positions (step si), bh positions (step si), bn images}, 128B swizzle,
+// out-of-bounds (padding) elements read as zero.  boxDim = count * elementStride as cuTensorMapEncodeTiled specifies.
+int get_tmap_im2col_f32(const void* ptr, int n_img, int Hs, int Ws, int C, int bn, int bh, int bw, int si,
+                        CUtensorMap* out) {
+  using Key = std::tuple<const void*, int, int, int, int, int, int, int, int>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  Key key{ptr, n_img, Hs, Ws, C, bn, bh, bw, si};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MDGAN_ERR_DRIVER;
+  if (C % 32 != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || bw * si > 256 || bh * si > 256 || bn > 256 ||
+      bn * bh * bw != 128)
+    return MDGAN_ERR_BAD_ARG;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)n_img};
+  cuuint64_t gstride[3] = {(cuuint64_t)C * 4, (cuuint64_t)Ws * C * 4, (cuuint64_t)Hs * Ws * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)(bw * si), (cuuint32_t)(bh * si), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)si, (cuuint32_t)si, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return MDGAN_ERR_DRIVER;
+  cache[key] = m;
+  *out = m;
+  return 0;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("MDGAN_PDL");  // opt-in: measured on B200 (round 1) it does not shorten the captured step

@@ -62,6 +62,10 @@ inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
 // Returns 0 on success.  Maps are cached per (ptr, rows, cols, box_rows).
 int get_tmap_2d_f32(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, CUtensorMap* out);
 
+// 4-D im2col-tile map over an NHWC fp32 tensor (see common.cu).  Cached per argument tuple.
+int get_tmap_im2col_f32(const void* ptr, int n_img, int Hs, int Ws, int C, int bn, int bh, int bw, int si,
+                        CUtensorMap* out);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace mdgan

@@ -390,9 +390,14 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-template <int BN>
+// TMA_A: the raw activation tile is fetched by ONE 4-D tiled TMA load per K step (tmap_a: box = the 128 im2col rows of
+// one tap x 32 channels, element strides = the conv stride, out-of-bounds = zero padding) instead of by the eight
+// loader warps: the tile then crosses the L1/shared-memory arrays once (the TMA write) instead of three times
+// (L1 fill, L1 read, shared store).  Possible whenever 128 consecutive rows of the (n, i, j) grid form a box.
+template <int BN, bool TMA_A>
 __global__ void __launch_bounds__(kTaThreads, 1)
-conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParams p) {
+conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
+                    const ConvGemmParams p) {
   using S = ConvTaSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -417,13 +422,14 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmPa
 
   pdl_trigger();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S::kRawStages; ++s) { mbar_init(&raw_full[s], kNumProducerWarps); mbar_init(&raw_empty[s], 4); }
+    for (int s = 0; s < S::kRawStages; ++s) { mbar_init(&raw_full[s], TMA_A ? 1 : kNumProducerWarps); mbar_init(&raw_empty[s], 4); }
     for (int s = 0; s < S::kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < S::kAStages; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
     mbar_init(tmem_full_bar, 1);
     fence_mbar_init();
   }
   if (warp == 12 && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (TMA_A && warp == 4 && lane == 0) tma_prefetch_desc(&tmap_a);
   if (warp == 13) tmem_alloc<S::kTmemCols>(tmem_ptr_smem);
   tc_fence_before_sync();
   __syncthreads();
@@ -466,62 +472,83 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmPa
     }
   } else if (warp < 4 + kNumProducerWarps) {
     // ------------------------------------------------------------------ loaders (raw fp32 tile), then epilogue
-    const int tid = threadIdx.x - 128;
-    const int chunk = tid & 7;
-    const int row_in = tid >> 3;  // 0..31
-    const int SI = (p.mode == 0) ? 2 : 1;
-    int base_off[4], sh0[4], sw0[4];
-    bool row_ok[4];
-    uint32_t soff[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = row_in + 32 * i;
-      const int m = m0 + r;
-      row_ok[i] = m < p.M;
-      const int mm = row_ok[i] ? m : 0;
-      const int img = mm / (p.Hg * p.Wg);
-      const int rem = mm - img * (p.Hg * p.Wg);
-      const int gi = rem / p.Wg, gj = rem - gi * p.Wg;
-      sh0[i] = gi * SI;
-      sw0[i] = gj * SI;
-      base_off[i] = ((img * p.Hs + sh0[i]) * p.Ws + sw0[i]) * p.C + chunk * 4;
-      soff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
-    }
-    const uint32_t raw0 = smem_u32(smem);
-    int tap_l = 0, cc_l = 0;
-    auto issue_loads = [&](float4(&buf)[4]) {
-      int dh, dw;
-      if (p.mode == 0) { dh = (tap_l >> 2) - 1; dw = (tap_l & 3) - 1; }
-      else if (p.mode == 1) { dh = ph - (tap_l >> 1); dw = pw - (tap_l & 1); }
-      else { dh = 0; dw = 0; }
-      const int tap_off = (dh * p.Ws + dw) * p.C + cc_l * kBK;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int sh = sh0[i] + dh, sw = sw0[i] + dw;
-        const bool ok = row_ok[i] && sh >= 0 && sh < p.Hs && sw >= 0 && sw < p.Ws;
-        buf[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.src + base_off[i] + tap_off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (++cc_l == cchunks) { cc_l = 0; ++tap_l; }
-    };
-    float4 buf[kPrefetch][4];
-#pragma unroll
-    for (int u = 0; u < kPrefetch; ++u)
-      if (u < ksteps) issue_loads(buf[u]);
-    int s = 0;
-    uint32_t par = 0;
-    for (int it0 = 0; it0 < ksteps; it0 += kPrefetch) {
-#pragma unroll
-      for (int u = 0; u < kPrefetch; ++u) {
-        const int it = it0 + u;
-        if (it < ksteps) {
+    if (TMA_A) {
+      if (warp == 4 && lane == 0) {
+        const int SIa = (p.mode == 0) ? 2 : 1;
+        const int n_start = m0 / (p.Hg * p.Wg);
+        const int h_start = (m0 - n_start * (p.Hg * p.Wg)) / p.Wg;
+        int s = 0, tap_l = 0, cc_l = 0;
+        uint32_t par = 0;
+        for (int it = 0; it < ksteps; ++it) {
+          int dh, dw;
+          if (p.mode == 0) { dh = (tap_l >> 2) - 1; dw = (tap_l & 3) - 1; }
+          else if (p.mode == 1) { dh = ph - (tap_l >> 1); dw = pw - (tap_l & 1); }
+          else { dh = 0; dw = 0; }
           mbar_wait(&raw_empty[s], par ^ 1);
-          const uint32_t stage = raw0 + s * S::kRawBytes;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) sts128(stage + soff[i], buf[u][i].x, buf[u][i].y, buf[u][i].z, buf[u][i].w);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&raw_full[s]);
-          if (it + kPrefetch < ksteps) issue_loads(buf[u]);
+          mbar_arrive_expect_tx(&raw_full[s], S::kRawBytes);
+          tma_load_4d(smem_u32(smem) + s * S::kRawBytes, &tmap_a, &raw_full[s], cc_l * kBK, dw, h_start * SIa + dh, n_start);
+          if (++cc_l == cchunks) { cc_l = 0; ++tap_l; }
           if (++s == S::kRawStages) { s = 0; par ^= 1; }
+        }
+      }
+    } else {
+      const int tid = threadIdx.x - 128;
+      const int chunk = tid & 7;
+      const int row_in = tid >> 3;  // 0..31
+      const int SI = (p.mode == 0) ? 2 : 1;
+      int base_off[4], sh0[4], sw0[4];
+      bool row_ok[4];
+      uint32_t soff[4];
+  #pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = row_in + 32 * i;
+        const int m = m0 + r;
+        row_ok[i] = m < p.M;
+        const int mm = row_ok[i] ? m : 0;
+        const int img = mm / (p.Hg * p.Wg);
+        const int rem = mm - img * (p.Hg * p.Wg);
+        const int gi = rem / p.Wg, gj = rem - gi * p.Wg;
+        sh0[i] = gi * SI;
+        sw0[i] = gj * SI;
+        base_off[i] = ((img * p.Hs + sh0[i]) * p.Ws + sw0[i]) * p.C + chunk * 4;
+        soff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
+      }
+      const uint32_t raw0 = smem_u32(smem);
+      int tap_l = 0, cc_l = 0;
+      auto issue_loads = [&](float4(&buf)[4]) {
+        int dh, dw;
+        if (p.mode == 0) { dh = (tap_l >> 2) - 1; dw = (tap_l & 3) - 1; }
+        else if (p.mode == 1) { dh = ph - (tap_l >> 1); dw = pw - (tap_l & 1); }
+        else { dh = 0; dw = 0; }
+        const int tap_off = (dh * p.Ws + dw) * p.C + cc_l * kBK;
+  #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int sh = sh0[i] + dh, sw = sw0[i] + dw;
+          const bool ok = row_ok[i] && sh >= 0 && sh < p.Hs && sw >= 0 && sw < p.Ws;
+          buf[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.src + base_off[i] + tap_off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (++cc_l == cchunks) { cc_l = 0; ++tap_l; }
+      };
+      float4 buf[kPrefetch][4];
+  #pragma unroll
+      for (int u = 0; u < kPrefetch; ++u)
+        if (u < ksteps) issue_loads(buf[u]);
+      int s = 0;
+      uint32_t par = 0;
+      for (int it0 = 0; it0 < ksteps; it0 += kPrefetch) {
+  #pragma unroll
+        for (int u = 0; u < kPrefetch; ++u) {
+          const int it = it0 + u;
+          if (it < ksteps) {
+            mbar_wait(&raw_empty[s], par ^ 1);
+            const uint32_t stage = raw0 + s * S::kRawBytes;
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) sts128(stage + soff[i], buf[u][i].x, buf[u][i].y, buf[u][i].z, buf[u][i].w);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_full[s]);
+            if (it + kPrefetch < ksteps) issue_loads(buf[u]);
+            if (++s == S::kRawStages) { s = 0; par ^= 1; }
+          }
         }
       }
     }
@@ -584,17 +611,28 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmPa
   }
 }
 
-template <int BN>
-static int launch_conv_gemm_ta(const CUtensorMap& tmap, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
+template <int BN, bool TMA_A>
+static int launch_conv_gemm_ta(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p, dim3 grid,
+                               cudaStream_t st) {
   using S = ConvTaSmem<BN>;
   static_assert(S::kDynamic <= 227 * 1024, "shared memory per CTA");
   static bool configured = false;
   if (!configured) {
-    MDGAN_CUDA(cudaFuncSetAttribute(conv_gemm_ta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
+    MDGAN_CUDA(cudaFuncSetAttribute(conv_gemm_ta_kernel<BN, TMA_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    S::kDynamic));
     configured = true;
   }
-  MDGAN_LAUNCH((conv_gemm_ta_kernel<BN>), grid, dim3(kTaThreads), S::kDynamic, st, tmap, p);
+  MDGAN_LAUNCH((conv_gemm_ta_kernel<BN, TMA_A>), grid, dim3(kTaThreads), S::kDynamic, st, tmap, tmap_a, p);
   return 0;
+}
+
+// MDGAN_CONV_TMA = 1 (default) | 0: fetch the activation tile with tiled TMA loads where the row tile is a box.
+static bool conv_tma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MDGAN_CONV_TMA");
+    return e ? e[0] != '0' : true;
+  }();
+  return on;
 }
 
 // MDGAN_CONV_TA = 1 (default) | 0: activation operand through tensor memory (tf32x3 only; same arithmetic, same bits).
@@ -678,11 +716,32 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   dim3 grid(row_tiles, N_pad / bn, phases);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x3 && conv_ta_enabled()) {
+    // 128 consecutive rows of the (n, i, j) grid are a box when whole images (128 % (Hg*Wg) == 0) or whole grid rows
+    // of one image (128 % Wg == 0 and Hg % (128 / Wg) == 0) fill the tile: then one tiled TMA load fetches it
+    int bn_img = 0, bh = 0, bw = 0;
+    const int rows_img = Hg * Wg;
+    if (rows_img <= kBM && kBM % rows_img == 0) { bn_img = kBM / rows_img; bh = Hg; bw = Wg; }
+    else if (Wg <= kBM && kBM % Wg == 0 && Hg % (kBM / Wg) == 0) { bn_img = 1; bh = kBM / Wg; bw = Wg; }
+    CUtensorMap tmap_a = tmap;
+    bool tma_a = conv_tma_enabled() && bn_img > 0;
+    if (tma_a) {
+      const int si = mode == 0 ? 2 : 1;
+      tma_a = get_tmap_im2col_f32(src, n_img, Hs, Ws, C, bn_img, bh, bw, si, &tmap_a) == 0;
+    }
+    if (tma_a) {
+      switch (bn) {
+        case 128: return launch_conv_gemm_ta<128, true>(tmap, tmap_a, p, grid, st);
+        case 64: return launch_conv_gemm_ta<64, true>(tmap, tmap_a, p, grid, st);
+        case 32: return launch_conv_gemm_ta<32, true>(tmap, tmap_a, p, grid, st);
+        case 16: return launch_conv_gemm_ta<16, true>(tmap, tmap_a, p, grid, st);
+        default: return MDGAN_ERR_UNSUPPORTED;
+      }
+    }
     switch (bn) {
-      case 128: return launch_conv_gemm_ta<128>(tmap, p, grid, st);
-      case 64: return launch_conv_gemm_ta<64>(tmap, p, grid, st);
-      case 32: return launch_conv_gemm_ta<32>(tmap, p, grid, st);
-      case 16: return launch_conv_gemm_ta<16>(tmap, p, grid, st);
+      case 128: return launch_conv_gemm_ta<128, false>(tmap, tmap_a, p, grid, st);
+      case 64: return launch_conv_gemm_ta<64, false>(tmap, tmap_a, p, grid, st);
+      case 32: return launch_conv_gemm_ta<32, false>(tmap, tmap_a, p, grid, st);
+      case 16: return launch_conv_gemm_ta<16, false>(tmap, tmap_a, p, grid, st);
       default: return MDGAN_ERR_UNSUPPORTED;
     }
   }

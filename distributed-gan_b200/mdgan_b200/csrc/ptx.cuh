@@ -84,6 +84,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+// 4D tiled load: coordinates innermost first (c, w, h, n); may be negative (out-of-bounds elements read as zero).
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 template <uint32_t NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
