@@ -73,7 +73,7 @@ int get_tmap_im2col_f32(const void* ptr, int n_img, int Hs, int Ws, int C, int b
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MDGAN_ERR_DRIVER;
   if (C % 32 != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || bw * si > 256 || bh * si > 256 || bn > 256 ||
-      bn * bh * bw != 128)
+      bn * bh * bw > 128 || bn * bh * bw < 1)
     return MDGAN_ERR_BAD_ARG;
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)n_img};
   cuuint64_t gstride[3] = {(cuuint64_t)C * 4, (cuuint64_t)Ws * C * 4, (cuuint64_t)Hs * Ws * C * 4};

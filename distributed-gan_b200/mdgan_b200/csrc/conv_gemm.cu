@@ -44,6 +44,8 @@ struct ConvGemmParams {
   int round_tf32;     // 1: store outputs rounded to TF32 (they feed another tensor-core operand)
   int accumulate;     // 1: dst += result (NCHW outputs only; sums feedbacks of workers sharing a batch)
   int lo_row_offset;  // tf32x3: row offset of the `lo` half of the packed weights
+  int rows_per_tile;  // GEMM rows a CTA owns: 128, or fewer when a TMA box of whole images does not fill 128 rows (the
+                      // remaining TMEM lanes carry garbage that is never stored)
   const float* gate;  // optional, NHWC like dst: dst = result * act'(gate) (backward of the activation that produced
   int gate_act;       //   `gate`, fused into the data-gradient GEMM that feeds it; 1 ReLU, 2 LeakyReLU(gate_slope))
   float gate_slope;
@@ -99,7 +101,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvGemmParams& p, uint32_t 
   if (BN >= 32 || half == 0) {
     const int row = q * 32 + lane;
     const int m = m0 + row;
-    const bool ok = m < p.M;
+    const bool ok = m < p.M && row < p.rows_per_tile;
     const int mm = ok ? m : 0;
     const int img = mm / (p.Hg * p.Wg);
     const int rem = mm - img * (p.Hg * p.Wg);
@@ -190,7 +192,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM;
+  const int m0 = blockIdx.x * p.rows_per_tile;
   const int n0 = blockIdx.y * BN;
   const int phase = blockIdx.z;  // UP: output parity phase (ph*2 + pw)
   const int ph = phase >> 1, pw = phase & 1;
@@ -412,7 +414,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM;
+  const int m0 = blockIdx.x * p.rows_per_tile;
   const int n0 = blockIdx.y * BN;
   const int phase = blockIdx.z;
   const int ph = phase >> 1, pw = phase & 1;
@@ -485,7 +487,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
           else if (p.mode == 1) { dh = ph - (tap_l >> 1); dw = pw - (tap_l & 1); }
           else { dh = 0; dw = 0; }
           mbar_wait(&raw_empty[s], par ^ 1);
-          mbar_arrive_expect_tx(&raw_full[s], S::kRawBytes);
+          mbar_arrive_expect_tx(&raw_full[s], p.rows_per_tile * 128);
           tma_load_4d(smem_u32(smem) + s * S::kRawBytes, &tmap_a, &raw_full[s], cc_l * kBK, dw, h_start * SIa + dh, n_start);
           if (++cc_l == cchunks) { cc_l = 0; ++tap_l; }
           if (++s == S::kRawStages) { s = 0; par ^= 1; }
@@ -626,6 +628,15 @@ static int launch_conv_gemm_ta(const CUtensorMap& tmap, const CUtensorMap& tmap_
   return 0;
 }
 
+// MDGAN_CONV_TMA_PARTIAL = 1 (default) | 0: also use TMA boxes of whole images that do not fill 128 rows (7x7 grids).
+static bool conv_tma_partial_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MDGAN_CONV_TMA_PARTIAL");
+    return e ? e[0] != '0' : true;
+  }();
+  return on;
+}
+
 // MDGAN_CONV_TMA = 1 (default) | 0: fetch the activation tile with tiled TMA loads where the row tile is a box.
 static bool conv_tma_enabled() {
   static const bool on = [] {
@@ -692,8 +703,18 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   if (p.M <= 0) return MDGAN_ERR_BAD_ARG;
   const int taps = mode == 0 ? 16 : (mode == 1 ? 4 : 1);
   const int phases = mode == 1 ? 4 : 1;
-  const int row_tiles = ceil_div(p.M, kBM);
   if (precision != 0 && precision != 1) return MDGAN_ERR_BAD_ARG;
+  // TMA-fed activation tile (tf32x3 TMEM-operand kernel): the rows of a CTA must be a box of the (n, i, j) grid --
+  // whole images (as many as fit in 128 rows; 7x7 grids give 98-row tiles) or whole grid rows of one image.
+  int bn_img = 0, bh = 0, bw = 0;
+  p.rows_per_tile = kBM;
+  if (precision == 1 && conv_ta_enabled() && conv_tma_enabled()) {
+    const int rows_img = Hg * Wg;
+    if (rows_img <= kBM && (kBM % rows_img == 0 || conv_tma_partial_enabled())) { bn_img = kBM / rows_img; bh = Hg; bw = Wg; }
+    else if (Wg <= kBM && kBM % Wg == 0 && Hg % (kBM / Wg) == 0) { bn_img = 1; bh = kBM / Wg; bw = Wg; }
+    if (bn_img > 0) p.rows_per_tile = bn_img * bh * bw;
+  }
+  const int row_tiles = ceil_div(p.M, p.rows_per_tile);
   const bool x3 = precision == 1;
   // Tile width: the candidate (dividing N_pad) with the lowest estimated time -- wide tiles use the tensor core
   // better, narrow ones fill the 148 SMs when the row grid is small.
@@ -716,17 +737,12 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   dim3 grid(row_tiles, N_pad / bn, phases);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x3 && conv_ta_enabled()) {
-    // 128 consecutive rows of the (n, i, j) grid are a box when whole images (128 % (Hg*Wg) == 0) or whole grid rows
-    // of one image (128 % Wg == 0 and Hg % (128 / Wg) == 0) fill the tile: then one tiled TMA load fetches it
-    int bn_img = 0, bh = 0, bw = 0;
-    const int rows_img = Hg * Wg;
-    if (rows_img <= kBM && kBM % rows_img == 0) { bn_img = kBM / rows_img; bh = Hg; bw = Wg; }
-    else if (Wg <= kBM && kBM % Wg == 0 && Hg % (kBM / Wg) == 0) { bn_img = 1; bh = kBM / Wg; bw = Wg; }
     CUtensorMap tmap_a = tmap;
-    bool tma_a = conv_tma_enabled() && bn_img > 0;
+    bool tma_a = bn_img > 0;
     if (tma_a) {
       const int si = mode == 0 ? 2 : 1;
-      tma_a = get_tmap_im2col_f32(src, n_img, Hs, Ws, C, bn_img, bh, bw, si, &tmap_a) == 0;
+      rc = get_tmap_im2col_f32(src, n_img, Hs, Ws, C, bn_img, bh, bw, si, &tmap_a);
+      if (rc != 0) return rc;  // the tiling above already committed to the box
     }
     if (tma_a) {
       switch (bn) {
