@@ -349,6 +349,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
   }
   __syncthreads();
   if (warp == 9) {
+    __syncwarp();
     tc_fence_after_sync();
     tmem_dealloc<S::kTmemCols>(tmem_base);
   }
@@ -454,11 +455,12 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         const float4 v = lds128(row_base + s * S::kRawBytes + ((c ^ (r & 7)) << 4));
         x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&raw_empty[s]);   // the row is in registers: the loaders may refill the stage
       float hi[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) hi[j] = tf32_round_fast(x[j]);
+      for (int j = 0; j < 32; ++j) hi[j] = tf32_round_fast(x[j]);   // consumes every loaded word: the loads have landed
+      fence_proxy_async_smem();                    // order the generic-proxy reads before the next TMA write of the stage
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[s]);   // the row is in registers: the stage may be refilled
       mbar_wait(&a_empty[t], part ^ 1);            // the MMAs that read this TMEM stage have completed
       tc_fence_after_sync();
       tmem_st_x32(t_lane + t * 64, hi);
@@ -554,6 +556,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         }
       }
     }
+    __syncwarp();  // warp 4's lane 0 was issuing TMA loads: converge before the warp-aligned tcgen05.ld below
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after_sync();
     conv_epilogue<BN, S::kAccs>(p, tmem_base, warp & 3, (warp - 4) >> 2, lane, m0, n0, ph, pw);
@@ -608,6 +611,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   }
   __syncthreads();
   if (warp == 13) {
+    __syncwarp();
     tc_fence_after_sync();
     tmem_dealloc<S::kTmemCols>(tmem_base);
   }

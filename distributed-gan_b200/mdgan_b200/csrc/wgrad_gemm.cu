@@ -14,6 +14,8 @@
 // accepts for 32-bit operands).  One tcgen05.mma (K = 8 pixels) consumes two 4-row atoms of every group.
 // Split-K over pixels fills the machine; partial sums go to [split][tap][C1][C2] and are reduced (in a fixed
 // order, deterministically) by the unpack kernel in elementwise.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -258,9 +260,291 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
   }
   __syncthreads();
   if (warp == kWProducerWarps) {
+    __syncwarp();
     tc_fence_after_sync();
     tmem_dealloc<S::kTmemCols>(tmem_base);
   }
+}
+
+// ================================================================================================================
+// tf32x3 variant with the Lo operand (the M side: 128 channels x 32 pixels per K step) in tensor memory.  The raw fp32
+// tile [32 pixels][128 channels] arrives by TMA (four 2-D boxes of 32 pixels x 32 channels, 128B swizzle, pixels past
+// the end read as zero); transposer warp q owns channel group q = TMEM lane quarter q: a thread reads ITS channel of
+// the 32 pixel rows (a warp reads 32 consecutive words of a row: conflict-free under the swizzle), splits hi / lo in
+// registers and writes its TMEM lane (tcgen05.st).  The MMAs read A from TMEM; only the Hi operand (N side) is still
+// produced through shared memory by the eight producer warps.  Shared-memory/L1 traffic per K step: 32 KB for Lo
+// (TMA write + one read) instead of 112 KB (L1 fill + read, hi/lo stores, three MMA reads).
+//   warps 0-3 : transposers            warps 4-11: Hi producers, then the epilogue
+//   warp 12   : Lo TMA issuer (lane 0) + TMEM allocator + single-thread MMA issuer (lane 0 of warp 13)
+constexpr int kWTaThreads = (4 + kWProducerWarps + 2) * 32;
+
+template <int BN>
+struct WgradTaSmem {
+  static constexpr int kBBytes = (BN / 32) * kWK * 128;   // one of hi / lo
+  static constexpr int kStageBytes = 2 * kBBytes;         // [B_hi | B_lo]
+  static constexpr int kStages = 3;
+  static constexpr int kRawBytes = (kWM / 32) * kWK * 128;  // 16 KB raw Lo tile
+  static constexpr int kRawStages = 3;
+  static constexpr int kAStages = BN > 64 ? 2 : 3;        // TMEM stages of [A_hi (32 columns) | A_lo (32 columns)]
+  static constexpr int kRawOff = kStages * kStageBytes;
+  static constexpr int kBarOffset = kRawOff + kRawStages * kRawBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kStages + 2 * kRawStages + 2 * kAStages + 1) * 8 + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+  static constexpr int kMain = BN > 64 ? 2 : 4;
+  static constexpr int kAccs = kMain + 1;
+  static constexpr int kACol0 = kAccs * BN;
+  static constexpr uint32_t kTmemCols = 512;
+  static_assert(kACol0 + kAStages * 64 <= 512, "TMEM holds 512 columns");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kWTaThreads, 1)
+wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradParams p) {
+  using S = WgradTaSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* b_empty = b_full + S::kStages;
+  uint64_t* raw_full = b_empty + S::kStages;
+  uint64_t* raw_empty = raw_full + S::kRawStages;
+  uint64_t* a_full = raw_empty + S::kRawStages;
+  uint64_t* a_empty = a_full + S::kAStages;
+  uint64_t* tmem_full_bar = a_empty + S::kAStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int c1_0 = blockIdx.x * kWM;
+  const int c2_0 = blockIdx.y * BN;
+  const int tap = blockIdx.z / p.splits;
+  const int split = blockIdx.z - tap * p.splits;
+  const int pix0 = split * p.pix_per_split;
+  const int pix1 = min(p.P, pix0 + p.pix_per_split);
+  const int ksteps = (pix1 > pix0) ? (pix1 - pix0 + kWK - 1) / kWK : 0;
+  const int dh = (p.mode == 0) ? (tap >> 2) - 1 : 0;
+  const int dw = (p.mode == 0) ? (tap & 3) - 1 : 0;
+  const int SI = (p.mode == 0) ? 2 : 1;
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S::kStages; ++s) { mbar_init(&b_full[s], kWProducerWarps); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < S::kRawStages; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+    for (int s = 0; s < S::kAStages; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 12 && lane == 0) tma_prefetch_desc(&tmap_lo);
+  if (warp == 13) tmem_alloc<S::kTmemCols>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- transposers: raw Lo tile -> TMEM lane (= channel)
+    const uint32_t grp = smem_u32(smem) + S::kRawOff + warp * (kWK * 128);  // this warp's 32-channel group
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + S::kACol0;
+    const uint32_t cword = (lane & 3) * 4, cchunk = lane >> 2;
+    int s = 0, t = 0;
+    uint32_t pars = 0, part = 0;
+    for (int it = 0; it < ksteps; ++it) {
+      mbar_wait(&raw_full[s], pars);
+      float x[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const uint32_t addr = grp + s * S::kRawBytes + r * 128 + ((cchunk ^ (r & 7)) << 4) + cword;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[r]) : "r"(addr));
+      }
+      float hi[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) hi[j] = tf32_round_fast(x[j]);   // consumes every loaded word: the loads have landed
+      fence_proxy_async_smem();                    // generic-proxy reads before the next TMA write of this stage
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[s]);
+      mbar_wait(&a_empty[t], part ^ 1);
+      tc_fence_after_sync();
+      tmem_st_x32(t_lane + t * 64, hi);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] -= hi[j];
+      tmem_st_x32(t_lane + t * 64 + 32, x);
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[t]);
+      if (++s == S::kRawStages) { s = 0; pars ^= 1; }
+      if (++t == S::kAStages) { t = 0; part ^= 1; }
+    }
+  } else if (warp < 4 + kWProducerWarps) {
+    // ---------------------------------------------------------------- Hi producers (shared memory), then epilogue
+    const int tid = threadIdx.x - 128;
+    const uint32_t smem0 = smem_u32(smem);
+    constexpr int kBChunksPerRow = BN / 4;
+    constexpr int kBRowsPerPass = 256 / kBChunksPerRow;
+    constexpr int kBPasses = kWK / kBRowsPerPass;
+    const int b_cidx = tid % kBChunksPerRow;
+    const int b_row0 = tid / kBChunksPerRow;
+    const int hw_l = p.Hl * p.Wl;
+    uint32_t b_soff[kBPasses];
+#pragma unroll
+    for (int i = 0; i < kBPasses; ++i) {
+      const int r = b_row0 + kBRowsPerPass * i;
+      b_soff[i] = (b_cidx >> 3) * (kWK * 128) + r * 128 + swz32(b_cidx & 7, r);
+    }
+    int pbase_l = pix0;
+    auto issue_loads = [&](float4(&bbuf)[kBPasses]) {
+#pragma unroll
+      for (int i = 0; i < kBPasses; ++i) {
+        const int pix = pbase_l + b_row0 + kBRowsPerPass * i;
+        bool ok = pix < pix1;
+        size_t off = 0;
+        if (ok) {
+          const int img = static_cast<int>((static_cast<unsigned long long>(pix) * p.magic_hw) >> 40);
+          const int rem = pix - img * hw_l;
+          const int gi = static_cast<int>((static_cast<unsigned long long>(rem) * p.magic_w) >> 40);
+          const int gj = rem - gi * p.Wl;
+          const int sh = gi * SI + dh, sw = gj * SI + dw;
+          ok = sh >= 0 && sh < p.Hh && sw >= 0 && sw < p.Wh;
+          off = (static_cast<size_t>((img * p.Hh + sh) * p.Wh + sw)) * p.C2 + c2_0 + b_cidx * 4;
+        }
+        bbuf[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.hi + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      pbase_l += kWK;
+    };
+    constexpr int kPf = 4;
+    float4 bbuf[kPf][kBPasses];
+#pragma unroll
+    for (int u = 0; u < kPf; ++u)
+      if (u < ksteps) issue_loads(bbuf[u]);
+    int s = 0;
+    uint32_t par = 0;
+    for (int it0 = 0; it0 < ksteps; it0 += kPf) {
+#pragma unroll
+      for (int u = 0; u < kPf; ++u) {
+        const int it = it0 + u;
+        if (it < ksteps) {
+          mbar_wait(&b_empty[s], par ^ 1);
+          const uint32_t stage = smem0 + s * S::kStageBytes;
+#pragma unroll
+          for (int i = 0; i < kBPasses; ++i) store_split<true>(stage + b_soff[i], S::kBBytes, bbuf[u][i]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&b_full[s]);
+          if (it + kPf < ksteps) issue_loads(bbuf[u]);
+          if (++s == S::kStages) { s = 0; par ^= 1; }
+        }
+      }
+    }
+    // epilogue: TMEM -> partial[split][tap]
+    if (ksteps > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after_sync();
+    }
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    constexpr int kColsPerHalf = BN / 2;
+    const int c1 = c1_0 + q * 32 + lane;
+    const int taps = gridDim.z / p.splits;
+    float* orow = p.partial + (static_cast<size_t>(split * taps + tap) * p.C1 + c1) * p.C2 + c2_0;
+#pragma unroll 1
+    for (int c16 = 0; c16 < kColsPerHalf; c16 += 16) {
+      const int colx = half * kColsPerHalf + c16;
+      float v[16];
+      if (ksteps > 0) {
+        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + colx, v);
+        float tt[16];
+#pragma unroll
+        for (int a = 1; a < S::kAccs; ++a) {
+          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + colx, tt);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += tt[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+      if (c1 < p.C1) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(orow + colx + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    tc_fence_before_sync();
+  } else if (warp == 12) {
+    // ---------------------------------------------------------------- Lo TMA issuer: 4 boxes of 32 pixels x 32 channels
+    if (lane == 0) {
+      int s = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < ksteps; ++it) {
+        mbar_wait(&raw_empty[s], par ^ 1);
+        mbar_arrive_expect_tx(&raw_full[s], S::kRawBytes);
+        const uint32_t dst = smem_u32(smem) + S::kRawOff + s * S::kRawBytes;
+#pragma unroll
+        for (int g = 0; g < kWM / 32; ++g)
+          tma_load_2d(dst + g * (kWK * 128), &tmap_lo, &raw_full[s], c1_0 + 32 * g, pix0 + it * kWK);
+        if (++s == S::kRawStages) { s = 0; par ^= 1; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- MMA issuer: A from TMEM, B (MN-major) from smem
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kWM, BN, 0, 1);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem), p.lbo_b, p.sbo_b, 1);
+      constexpr uint64_t kStageStep = S::kStageBytes >> 4, kLoStep = S::kBBytes >> 4;
+      const uint32_t acc_corr = tmem_base + S::kMain * BN;
+      int s = 0, t = 0;
+      uint32_t par = 0, part = 0;
+      uint64_t db0 = bdesc0;
+      for (int it = 0; it < ksteps; ++it) {
+        mbar_wait(&a_full[t], part);
+        mbar_wait(&b_full[s], par);
+        tc_fence_after_sync();
+        const uint32_t acc = it != 0 ? 1u : 0u;
+        const uint32_t a_hi0 = tmem_base + S::kACol0 + t * 64;
+#pragma unroll
+        for (int k = 0; k < kWK / 8; ++k) {
+          const uint32_t a_hi = a_hi0 + 8 * k, a_lo = a_hi + 32;
+          const uint64_t db = db0 + 64 * k;  // 8 pixels = two 512-byte k-atoms
+          umma_tf32_ts(acc_corr, a_lo, db, idesc, k == 0 ? acc : 1u);
+          umma_tf32_ts(acc_corr, a_hi, db + kLoStep, idesc, 1u);
+          umma_tf32_ts(tmem_base + (k % S::kMain) * BN, a_hi, db, idesc, k < S::kMain ? acc : 1u);
+        }
+        umma_commit(&a_empty[t]);
+        umma_commit(&b_empty[s]);
+        db0 += kStageStep;
+        if (++s == S::kStages) { s = 0; par ^= 1; db0 = bdesc0; }
+        if (++t == S::kAStages) { t = 0; part ^= 1; }
+      }
+      if (ksteps > 0) umma_commit(tmem_full_bar);
+    }
+  }
+  __syncthreads();
+  if (warp == 13) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc<S::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_wgrad_ta(const CUtensorMap& tmap_lo, const WgradParams& p, dim3 grid, cudaStream_t st) {
+  using S = WgradTaSmem<BN>;
+  static_assert(S::kDynamic <= 227 * 1024, "shared memory per CTA");
+  static bool configured = false;
+  if (!configured) {
+    MDGAN_CUDA(cudaFuncSetAttribute(wgrad_gemm_ta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
+    configured = true;
+  }
+  MDGAN_LAUNCH((wgrad_gemm_ta_kernel<BN>), grid, dim3(kWTaThreads), S::kDynamic, st, tmap_lo, p);
+  return 0;
+}
+
+// MDGAN_WGRAD_TA = 1 (default) | 0: Lo operand by TMA into tensor memory (tf32x3 only; same arithmetic, same bits).
+static bool wgrad_ta_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MDGAN_WGRAD_TA");
+    return e ? e[0] != '0' : true;
+  }();
+  return on;
 }
 
 template <int BN, int STAGES, bool X3>
@@ -330,6 +614,12 @@ extern "C" int mdgan_wgrad_gemm(const float* lo, const float* hi, float* partial
   dim3 grid(C1 / kWM, C2 / bn, taps * splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision != 0 && precision != 1) return MDGAN_ERR_BAD_ARG;
+  if (precision == 1 && wgrad_ta_enabled()) {
+    CUtensorMap tmap_lo;
+    const int rc = get_tmap_2d_f32(lo, static_cast<uint64_t>(p.P), static_cast<uint64_t>(C1), kWK, &tmap_lo);
+    if (rc != 0) return rc;
+    return bn == 128 ? launch_wgrad_ta<128>(tmap_lo, p, grid, st) : launch_wgrad_ta<64>(tmap_lo, p, grid, st);
+  }
   if (precision == 1) return bn == 128 ? launch_wgrad<128, 3, true>(p, grid, st) : launch_wgrad<64, 4, true>(p, grid, st);
   return bn == 128 ? launch_wgrad<128, 6, false>(p, grid, st) : launch_wgrad<64, 6, false>(p, grid, st);
 }

@@ -9,12 +9,6 @@
 
 using namespace mdgan;
 
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -27,7 +21,6 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const float* v) {
                "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24); }
 
@@ -50,21 +43,28 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int nacc, int reps,
   const uint32_t tb = tptr;
   if (threadIdx.x == 0) {
     const uint32_t a_addr = smem_u32(smem), b_addr = a_addr + 16384;
-    const uint32_t idesc = MODE == 2 ? idesc_bf16(128, N) : make_idesc_tf32(128, N, 0, 0);
+    // MODE 3: both operands MN-major (SWIZZLE_128B_BASE32B, the weight-gradient layout); MODE 4: A from TMEM, B MN-major
+    const uint32_t idesc = MODE == 2 ? idesc_bf16(128, N) : MODE == 3 ? make_idesc_tf32(128, N, 1, 1)
+                           : MODE == 4 ? make_idesc_tf32(128, N, 0, 1) : make_idesc_tf32(128, N, 0, 0);
     const uint32_t a_tmem = tb + 448;
     uint64_t da[4], db[4];
     uint32_t d[2] = {tb, tb + (nacc > 1 ? (uint32_t)N : 0u)};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      da[k] = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-      db[k] = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+      if (MODE >= 3) {  // 8 pixels = two 512-byte k-atoms; LBO = 4096 (32-channel groups), SBO = 512
+        da[k] = make_smem_desc_sw128(a_addr + k * 1024, 4096, 512, 1);
+        db[k] = make_smem_desc_sw128(b_addr + k * 1024, 4096, 512, 1);
+      } else {
+        da[k] = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+        db[k] = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+      }
     }
     long long t0 = clock64();
     for (int r = 0; r < reps; r += 8) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        if (MODE == 0) umma_tf32(d[u & 1], da[u & 3], db[u & 3], idesc, 1u);
-        else if (MODE == 1) umma_tf32_ts(d[u & 1], a_tmem + (u & 3) * 8, db[u & 3], idesc, 1u);
+        if (MODE == 0 || MODE == 3) umma_tf32(d[u & 1], da[u & 3], db[u & 3], idesc, 1u);
+        else if (MODE == 1 || MODE == 4) umma_tf32_ts(d[u & 1], a_tmem + (u & 3) * 8, db[u & 3], idesc, 1u);
         else umma_f16_ss(d[u & 1], da[u & 3], db[u & 3], idesc, 1u);
       }
     }
@@ -161,17 +161,21 @@ int main() {
   }
   // ---- rates
   const int reps = 4096;
-  const char* names[] = {"SS tf32", "TS tf32", "SS bf16"};
+  const char* names[] = {"SS tf32", "TS tf32", "SS bf16", "SS tf32 MN-major A+B", "TS tf32 MN-major B"};
   cudaFuncSetAttribute(rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int mode = 0; mode < 3; ++mode)
+  cudaFuncSetAttribute(rate_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(rate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int mode = 0; mode < 5; ++mode)
     for (int N : {16, 32, 64, 128, 256})
       for (int nacc : {1, 2}) {
         if (nacc * N > 448) continue;
         if (mode == 0) rate_kernel<0><<<148, 128, smem>>>(N, nacc, reps, d_out);
         else if (mode == 1) rate_kernel<1><<<148, 128, smem>>>(N, nacc, reps, d_out);
-        else rate_kernel<2><<<148, 128, smem>>>(N, nacc, reps, d_out);
+        else if (mode == 2) rate_kernel<2><<<148, 128, smem>>>(N, nacc, reps, d_out);
+        else if (mode == 3) rate_kernel<3><<<148, 128, smem>>>(N, nacc, reps, d_out);
+        else rate_kernel<4><<<148, 128, smem>>>(N, nacc, reps, d_out);
         cudaError_t e = cudaDeviceSynchronize();
         long long c = 0;
         cudaMemcpy(&c, d_out, 8, cudaMemcpyDeviceToHost);
