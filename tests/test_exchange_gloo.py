@@ -148,6 +148,51 @@ def test_two_process_gloo_run_matches_single_process(tmp_path):
     assert all(partners[partners[n] - 1] - 1 == n for n in range(N))
 
 
+def _single(prefetch: bool):
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200 import routing
+    from mdgan_b200.engine import EngineConfig, MDGANEngine
+
+    dataset = SyntheticImages(SHAPE, N * 4 * B)
+    shards = routing.split_dataset(len(dataset), N, True)
+    discs = {}
+    for n in range(N):
+        torch.manual_seed(100 + n)
+        discs[n] = nn.Linear(16, 1, bias=False)
+    torch.manual_seed(3)
+    gen = nn.Linear(Z, 16, bias=False)
+    streams = {n: routing.RealBatchStream(dataset, shards[n], B) for n in range(N)}
+    cfg = EngineConfig(n_workers=N, batch_size=B, z_dim=Z, image_shape=SHAPE, swap_interval=2, z_source="host",
+                       prefetch_host=prefetch)
+    eng = MDGANEngine(cfg, 0, 1, torch.device("cpu"), gen, discs, {n: streams[n].next for n in range(N)},
+                      factory=FakeFactory())
+    pairs, zs = [], []
+    for e in range(EPOCHS):
+        eng.iteration(e, last=(e == EPOCHS - 1))
+        pairs.append(None if eng.last_pairs is None else eng.last_pairs.clone())
+        zs.append(eng.gen.z.clone())
+    eng.sync_modules()
+    return gen.weight.detach().clone(), eng.X.clone(), pairs, zs, torch.get_rng_state()
+
+
+def test_host_prefetch_keeps_the_reference_rng_order():
+    """prefetch_host stages iteration e+1's noise while iteration e runs, except across a swap draw (the reference
+    draws the permutation before the next noise batch, server.py:321 vs :219) and after the last iteration: the noise
+    batches, swap pairs, results and the final state of the global RNG must not change."""
+    a, b = _single(False), _single(True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert all((p is None and q is None) or torch.equal(p, q) for p, q in zip(a[2], b[2]))
+    assert all(torch.equal(p, q) for p, q in zip(a[3], b[3]))
+    assert torch.equal(a[4], b[4]), "no extra draw from the global RNG"
+
+
+def test_make_exchange_on_cpu_is_the_collective_exchange():
+    from mdgan_b200.exchange import Exchange, make_exchange
+
+    ex = make_exchange(0, 1, 2, torch.device("cpu"), 2, 4, SHAPE)
+    assert type(ex) is Exchange and ex.mode == "nccl"
+
+
 def test_exchange_refuses_uninitialised_group():
     from mdgan_b200.exchange import Exchange
 
