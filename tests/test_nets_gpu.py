@@ -118,3 +118,17 @@ def test_generator_forward_backward(dev, name, n, prec):
             assert int(sd[k]) == int(ref_sd[k]) == 1
         elif "running" in k:
             assert relerr(sd[k], ref_sd[k]) < rtol, k
+
+
+@pytest.mark.parametrize("name,n", [("CIFAR10", 128), ("MNIST_DCGAN", 64)])
+def test_forward_backward_bitwise_repeatable(name, n):
+    """Every kernel has a fixed reduction order, so identical inputs must give identical BITS on every repetition
+    (generator forward/backward, discriminator training forward/backward, every intermediate buffer): the cheapest
+    detector of a race in the TMA / TMEM / mbarrier pipelines (tools/stress_repeat.py runs the long version)."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import stress_repeat
+
+    assert stress_repeat.run(name, n, 40) == 0
