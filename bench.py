@@ -380,8 +380,8 @@ def run_ours(args) -> None:
     traffic, traffic_note = None, None
     tpath = REPO / "profiles" / "r01_traffic.json"
     if tpath.exists() and args.dataset == "MNIST_DCGAN" and b == 64:
-        kname = "void wgrad_gemm_kernel" if top == "wgrad_gemm" else ("void conv_gemm_kernel" if tensor_bound else None)
-        rec = json.loads(tpath.read_text()).get("MNIST_DCGAN_b64", {}).get(kname)
+        kname = "void wgrad_gemm_ta_kernel" if top == "wgrad_gemm" else ("void conv_gemm_ta_kernel" if tensor_bound else None)
+        rec = json.loads(tpath.read_text()).get("MNIST_DCGAN_b64_final_kernels", {}).get(kname)
         if rec:
             traffic = rec["dram_bytes_per_launch_avg"]
             traffic_note = ("ncu --set full capture of this workload (profiles/r01_traffic.json), cold caches, average "
