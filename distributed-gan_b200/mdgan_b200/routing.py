@@ -16,6 +16,8 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import torch
 import torch.utils.data
 
@@ -78,12 +80,18 @@ class RealBatchStream:
     """worker.py:78-89,162-167 -- DataLoader(Subset(dataset, shard), b, shuffle=True, generator seed 0); the
     iterator is re-created on exhaustion.  Yields CPU fp32 [b, C, H, W] batches."""
 
-    def __init__(self, dataset, shard: torch.Tensor, batch_size: int):
+    def __init__(self, dataset, shard: torch.Tensor, batch_size: int, num_workers: Optional[int] = None):
+        """num_workers (default: MDGAN_LOADER_WORKERS, 0 like the reference): loader processes that decode /
+        transform samples ahead of the training loop.  The sampler, and therefore the order and content of the
+        batches, does not depend on it (the DataLoader returns batches in sampler order)."""
         g = torch.Generator()
         g.manual_seed(0)
         self.batch_size = batch_size
+        if num_workers is None:
+            num_workers = int(os.environ.get("MDGAN_LOADER_WORKERS", "0"))
+        kw = dict(num_workers=num_workers, prefetch_factor=4) if num_workers > 0 else {}
         self.loader = torch.utils.data.DataLoader(torch.utils.data.Subset(dataset, shard), batch_size=batch_size,
-                                                  shuffle=True, generator=g)
+                                                  shuffle=True, generator=g, **kw)
         self.it = iter(self.loader)
 
     def next(self) -> torch.Tensor:

@@ -78,6 +78,21 @@ def test_real_batch_stream_order_and_ragged():
         ragged.next()                                # 20 = 8 + 8 + 4: the reference would crash in BCELoss here
 
 
+def test_real_batch_stream_with_loader_workers_keeps_the_order():
+    """MDGAN_LOADER_WORKERS / num_workers only moves the sample transforms to loader processes: the batches are the
+    reference's batches, bit for bit, across the epoch boundary too."""
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200 import routing
+
+    ds = SyntheticImages((3, 8, 8), 48)
+    shard = routing.split_dataset(len(ds), 2, True)[1]
+    a = routing.RealBatchStream(ds, shard, 8, num_workers=0)
+    b = routing.RealBatchStream(ds, shard, 8, num_workers=2)
+    for _ in range(7):  # 3 batches per epoch: crosses two epoch boundaries
+        assert torch.equal(a.next(), b.next())
+    del b
+
+
 def test_placement_and_rank_parsing():
     from mdgan_b200 import routing
 
