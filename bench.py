@@ -464,6 +464,11 @@ def run_ours(args) -> None:
                    "l2": "512 MB buffer written between timed iterations (outside the per-step event pairs)",
                    "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+        "tensor_pipe_util": {"source": "committed ncu --set full captures, profiles/r01_ncu_full_conv_wgrad.md (not measured "
+                                       "by this run: ncu numbers are never bench values)",
+                             "metric": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                             "conv_128_wide_tiles_pct": [53, 75], "conv_64_wide_tiles_pct": [22, 30],
+                             "weight_gradient_pct": [22, 41]},
         "gpu_launches_per_step": launches_per_step, "per_op": shares,
     }
     emit(line)
