@@ -58,6 +58,10 @@ def test_bootstrap_single_gpu_matches_oracle(tmp_path, monkeypatch):
     assert [r["swap"] for r in srows] == ["False", "False", "True", "False", "True"]
     assert (tmp_path / "saved_images" / "real_images.png").exists()
     assert (tmp_path / "saved_images" / f"generated_epoch_{epochs - 1}.png").exists()
+    # the asynchronous snapshot of the last epoch (side-stream copy + writer thread) holds exactly the final state
+    g_last = torch.load(tmp_path / "weights" / f"generator_{epochs - 1}.pt")
+    assert list(g_last.keys()) == list(g.keys())
+    assert all(torch.equal(g_last[k], g[k]) and g_last[k].dtype == g[k].dtype and g_last[k].shape == g[k].shape for k in g)
 
 
 def test_standalone_matches_oracle(tmp_path, monkeypatch):
