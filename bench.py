@@ -6,8 +6,10 @@
     python bench.py --impl reference ...                       # the reference's CPU path (oracle port) on host cores
 
 Workload (DESIGN.md "Measurement"): MD-GAN with K = --gpus discriminator workers, one per GPU, the generator on
-rank 0 (north star "K=1/2/4/8 B200"), DCGAN on synthetic MNIST-shape 1x28x28 images, per-worker batch 64
-(BASELINE.json configs[1]); --dataset / --batch select the CIFAR-10 / CelebA shapes and the batch sweep.
+rank 0 (north star "K=1/2/4/8 B200"), the reference's CelebA-shape 3x64x64 DCGAN, per-worker batch 64 (BASELINE.json
+configs[3], the largest configuration that fits one GPU); --dataset / --batch / --swap-interval select the other
+configurations.  The JSON line also carries `shapes`: the device-timed step of the MNIST-shape DCGAN (configs[1]) and
+of the CIFAR-10-shape DCGAN with a discriminator swap EVERY iteration inside the timed window (configs[2]).
 A step = one generator iteration: G forward over k*b noise vectors -> every worker's D step (real + X_d, Adam) and
 error feedback on X_g -> feedback sum/reduce -> one G backward -> G Adam.  Per-GPU work is fixed as the number of
 GPUs grows (one more worker per GPU), i.e. weak scaling; `value` is the whole-job rate
@@ -49,10 +51,14 @@ LR, BETA_1, BETA_2 = 2e-4, 0.5, 0.999
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--dataset", default="MNIST_DCGAN", choices=["MNIST_DCGAN", "CIFAR10", "CelebA"])
+    ap.add_argument("--dataset", default="CelebA", choices=["MNIST_DCGAN", "CIFAR10", "CelebA"])
+    ap.add_argument("--swap-interval", type=int, default=0,
+                    help="discriminator swap every this many iterations INSIDE the timed window (0 = off)")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the per-shape sub-lines (MNIST / CIFAR-10 shape)")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the multi-GPU bit-identity pre-check (N > 1)")
     ap.add_argument("--batch", type=int, default=64, help="per-worker batch size b")
     ap.add_argument("--workers", type=int, default=0, help="discriminator workers (default: one per GPU)")
     ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"])
@@ -62,10 +68,13 @@ def parse_args():
     return ap.parse_args()
 
 
-def workload_name(args, n_workers: int) -> str:
+def workload_name(args, n_workers: int, dataset=None, swap=None) -> str:
     shape = {"MNIST_DCGAN": "MNIST-shape 1x28x28", "CIFAR10": "CIFAR-10-shape 3x32x32", "CelebA": "CelebA-shape 3x64x64"}
-    return (f"MD-GAN {shape[args.dataset]} DCGAN, K={n_workers} workers, per-worker batch {args.batch}, "
-            f"k=2 generated batches, Adam lr 2e-4 betas (0.5, 0.999), swap off in the timed window")
+    swap = args.swap_interval if swap is None else swap
+    swap_txt = f"discriminator swap every {swap} iteration(s) inside the timed window" if swap > 0 and n_workers > 1 \
+        else "swap off in the timed window"
+    return (f"MD-GAN {shape[dataset or args.dataset]} DCGAN, K={n_workers} workers, per-worker batch {args.batch}, "
+            f"k=2 generated batches, Adam lr 2e-4 betas (0.5, 0.999), {swap_txt}")
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -193,50 +202,11 @@ def build_generator(mod, seed):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args) -> None:
-    """The reference's own algorithm on the host CPU cores: the oracle port (oracle/mdgan_oracle.py, pinned bit-exact
-    to the unmodified reference run) with all the host threads torch can use.  Rank 0 only."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
-    import importlib
-
-    from datasets.DataPartitioner import SyntheticImages
-    from oracle.mdgan_oracle import OracleMDGAN
-
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n_workers = args.workers or args.gpus
-    mod = importlib.import_module(f"datasets.{args.dataset}")
-    dataset = SyntheticImages(mod.SHAPE, n_workers * 16 * args.batch)
-    oracle = OracleMDGAN(mod.Generator, mod.Discriminator, dataset, n_workers, args.batch, mod.Z_DIM, mod.SHAPE,
-                         seed=SEED, generator_lr=LR, discriminator_lr=LR, beta_1=BETA_1, beta_2=BETA_2)
-    t0 = time.perf_counter()
-    oracle.step(0, record=False)
-    first = time.perf_counter() - t0
-    warm = max(1, min(args.warmup, int(20.0 / max(first, 1e-3))))
-    steps = max(1, min(args.steps, int(120.0 / max(first, 1e-3))))
-    for e in range(1, warm):
-        oracle.step(e, record=False)
-    t0 = time.perf_counter()
-    for e in range(steps):
-        oracle.step(warm + e, record=False)
-    dt = (time.perf_counter() - t0) / steps
-    value = n_workers / dt
-    sample = (f"{steps} full iterations of the same workload (K={n_workers}, b={args.batch}) after {warm} warm-up, "
-              f"single process, torch CPU fp32 with {cores} intra-op threads")
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "generator_it_s": 1.0 / dt,
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, n_workers), "dataset": args.dataset, "batch": args.batch,
-                   "workers": n_workers},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit(line)
+REFERENCE_DATASETS = ("CIFAR10", "CelebA")   # plugins the reference ships with a DCGAN (MNIST_DCGAN is this repo's)
 
 
-def cpu_baseline(args, n_workers: int) -> dict:
+def _oracle_port_ms(args, n_workers: int, steps: int, warmup: int, budget_s: float):
+    """The oracle restatement (single process, all host threads).  Returns (ms_per_step, steps_run, warmup_run)."""
     import importlib
 
     from datasets.DataPartitioner import SyntheticImages
@@ -247,24 +217,99 @@ def cpu_baseline(args, n_workers: int) -> dict:
     mod = importlib.import_module(f"datasets.{args.dataset}")
     dataset = SyntheticImages(mod.SHAPE, n_workers * 16 * args.batch)
     rng = torch.get_rng_state()
+    swap = args.swap_interval if args.swap_interval > 0 else 10 ** 9
     oracle = OracleMDGAN(mod.Generator, mod.Discriminator, dataset, n_workers, args.batch, mod.Z_DIM, mod.SHAPE,
-                         seed=SEED, generator_lr=LR, discriminator_lr=LR, beta_1=BETA_1, beta_2=BETA_2)
+                         seed=SEED, generator_lr=LR, discriminator_lr=LR, beta_1=BETA_1, beta_2=BETA_2,
+                         swap_interval=swap)
     t0 = time.perf_counter()
     oracle.step(0, record=False)
     first = time.perf_counter() - t0
-    steps = max(2, min(200, int(args.cpu_seconds / max(first, 1e-3))))
-    oracle.step(1, record=False)
+    fit = int(budget_s / max(first, 1e-3))
+    warm = max(1, min(warmup, max(1, fit // 5)))
+    steps_run = max(1, min(steps, fit - warm))
+    for e in range(1, warm):
+        oracle.step(e, record=False)
     t0 = time.perf_counter()
-    for e in range(steps):
-        oracle.step(2 + e, record=False)
-    dt = (time.perf_counter() - t0) / steps
+    for e in range(steps_run):
+        oracle.step(warm + e, record=False)
+    dt = (time.perf_counter() - t0) / steps_run
     torch.set_rng_state(rng)
-    return {"value": n_workers / dt, "unit": UNIT, "generator_it_s": 1.0 / dt, "cores": cores, "kind": "port",
-            "sample": f"{steps} full iterations of the same workload (K={n_workers}, b={args.batch}) after 2 warm-up, "
-                      f"oracle port of server.py:213-333 + worker.py:157-284, torch CPU fp32, {cores} threads"}
+    return dt * 1e3, steps_run, warm
+
+
+def reference_cpu(args, n_workers: int, steps: int, warmup: int, budget_s: float) -> dict:
+    """The reference's own CPU implementation of the path on this host's cores.  kind "reference": the UNMODIFIED
+    reference sources (oracle/_ref, installed by oracle/ref_harness/install_ref.py) run as `bootstrap.py --backend gloo
+    --device cpu`, N+1 OS processes, OMP threads = floor(cores / (N+1)).  kind "port": the oracle
+    restatement in one process -- only for the MNIST-shape DCGAN, which the reference does not ship, or when
+    oracle/_ref is absent."""
+    cores = os.cpu_count() or 1
+    note = None
+    if args.dataset in REFERENCE_DATASETS:
+        try:
+            from oracle.ref_harness import time_reference
+
+            if time_reference.reference_src() is not None:
+                swap = args.swap_interval if args.swap_interval > 0 else 10 ** 9
+                r = time_reference.time_distributed(args.dataset, n_workers, args.batch, steps, warmup, swap_interval=swap,
+                                                    timeout_s=budget_s)
+                return {"ms_per_step": r["ms_per_step"], "steps": r["steps"], "warmup": r["warmup"], "cores": cores,
+                        "kind": "reference", "phases_ms": r["phases_ms"],
+                        "sample": (f"{r['steps']} generator iterations of the same workload (K={n_workers}, b={args.batch}) "
+                                   f"after {r['warmup']} warm-up, UNMODIFIED reference bootstrap.py --backend gloo --device cpu: "
+                                   f"{r['processes']} processes x {r['threads_per_process']} OMP threads on {cores} cores, server "
+                                   "CSV end.epoch_calculation - start.epoch_calculation")}
+            note = "oracle/_ref is not installed on this host"
+        except Exception as e:  # noqa: BLE001 -- time-out or a failed spawn: say so and fall back to the port
+            note = f"reference run failed ({type(e).__name__}: {str(e)[:200]})"
+    else:
+        note = f"the reference ships no {args.dataset} plugin"
+    ms, steps_run, warm = _oracle_port_ms(args, n_workers, steps, warmup, min(budget_s, 240.0))
+    return {"ms_per_step": ms, "steps": steps_run, "warmup": warm, "cores": cores, "kind": "port", "note": note,
+            "sample": (f"{steps_run} generator iterations of the same workload (K={n_workers}, b={args.batch}) after {warm} "
+                       f"warm-up, oracle port of server.py:213-333 + worker.py:157-284 in ONE process, torch CPU fp32, "
+                       f"{cores} intra-op threads ({note})")}
+
+
+def run_reference(args) -> None:
+    """`--impl reference`: the reference's CPU path with every host thread it can use.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n_workers = args.workers or args.gpus
+    r = reference_cpu(args, n_workers, args.steps, args.warmup, budget_s=780.0)
+    dt = r["ms_per_step"] * 1e-3
+    value = n_workers / dt
+    cpu = {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "generator_it_s": 1.0 / dt,
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, n_workers), "dataset": args.dataset, "batch": args.batch,
+                   "workers": n_workers, "swap_interval": args.swap_interval},
+        "cpu_baseline": cpu, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if r["steps"] != args.steps or r["warmup"] != args.warmup:
+        line["steps_note"] = (f"ran {r['steps']} steps / {r['warmup']} warm-up instead of the requested {args.steps} / "
+                              f"{args.warmup}: the CPU run is bounded to a few minutes")
+    if r.get("phases_ms"):
+        line["phases_ms"] = r["phases_ms"]
+    emit(line)
+
+
+def cpu_baseline(args, n_workers: int) -> dict:
+    """cpu_baseline of our arm's line (N = 1): a bounded sample (10 iterations after 2 warm-up) of the same workload."""
+    r = reference_cpu(args, n_workers, 10, 2, budget_s=max(60.0, 8 * args.cpu_seconds))
+    dt = r["ms_per_step"] * 1e-3
+    return {"value": n_workers / dt, "unit": UNIT, "generator_it_s": 1.0 / dt, "cores": r["cores"], "kind": r["kind"],
+            "sample": r["sample"], "phases_ms": r.get("phases_ms")}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def _profile_json(name: str):
+    path = REPO / "profiles" / name
+    return json.loads(path.read_text()) if path.exists() else None
+
+
 def run_ours(args) -> None:
     import importlib
 
@@ -290,24 +335,9 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     n_workers = args.workers or args.gpus
-    mod = importlib.import_module(f"datasets.{args.dataset}")
-    b, shape = args.batch, tuple(mod.SHAPE)
+    b = args.batch
     local = routing.workers_of_process(rank, world, n_workers)
-    dataset = SyntheticImages(shape, n_workers * 16 * b)  # M = N*16*b
-    shards = routing.split_dataset(len(dataset), n_workers, True)
-
-    def make_engine(resident: bool, z_source: str):
-        discs = build_modules(mod, local, SEED)
-        gen = build_generator(mod, SEED) if rank == 0 else None
-        cfg = EngineConfig(n_workers=n_workers, batch_size=b, z_dim=mod.Z_DIM, image_shape=shape, generator_lr=LR,
-                           discriminator_lr=LR, beta_1=BETA_1, beta_2=BETA_2, swap_interval=10 ** 9, local_epochs=1,
-                           z_source=z_source, prefetch_host=not resident)
-        if resident:
-            src = {n: DeviceResidentBatches(routing.RealBatchStream(dataset, shards[n], b), dev, shape, 16) for n in local}
-        else:
-            src = {n: _DeviceBatches(routing.RealBatchStream(dataset, shards[n], b), dev, shape) for n in local}
-        return MDGANEngine(cfg, rank, world, dev, gen, discs, src)
-
+    graphed = not args.no_graph
     flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)  # 512 MB > 126 MB L2
 
     def sync_all():
@@ -322,35 +352,72 @@ def run_ours(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    # ---------------------------------------------------------------- multi-GPU correctness pre-check
+    selfcheck = None
+    if world > 1 and not args.no_selfcheck:
+        from mdgan_b200.selfcheck import multi_gpu_bit_identity
+
+        selfcheck = multi_gpu_bit_identity(rank, world, dev, "CIFAR10", None, 16, 5, 2, graph=True, seed=SEED)
+        sync_all()
+
+    def make_engine(mod, dataset, shards, resident: bool, z_source: str, swap: int):
+        discs = build_modules(mod, local, SEED)
+        gen = build_generator(mod, SEED) if rank == 0 else None
+        shape = tuple(mod.SHAPE)
+        cfg = EngineConfig(n_workers=n_workers, batch_size=b, z_dim=mod.Z_DIM, image_shape=shape, generator_lr=LR,
+                           discriminator_lr=LR, beta_1=BETA_1, beta_2=BETA_2, swap_interval=swap if swap > 0 else 10 ** 9,
+                           local_epochs=1, z_source=z_source, prefetch_host=not resident)
+        if resident:
+            src = {n: DeviceResidentBatches(routing.RealBatchStream(dataset, shards[n], b), dev, shape, 16) for n in local}
+        else:
+            src = {n: _DeviceBatches(routing.RealBatchStream(dataset, shards[n], b), dev, shape) for n in local}
+        return MDGANEngine(cfg, rank, world, dev, gen, discs, src)
+
+    def device_leg(ds_name: str, swap: int, steps: int, warmup: int, sample_clocks: bool):
+        """`value` leg: inputs resident in HBM, the captured step (+ the host-driven swap when due) between CUDA events."""
+        mod = importlib.import_module(f"datasets.{ds_name}")
+        dataset = SyntheticImages(tuple(mod.SHAPE), n_workers * 16 * b)  # M = N*16*b (BASELINE.md section 2)
+        shards = routing.split_dataset(len(dataset), n_workers, True)
+        engine = make_engine(mod, dataset, shards, resident=True, z_source="device", swap=swap)
+        epoch = 0
+        for _ in range(max(warmup, 3)):
+            engine.iteration(epoch)
+            epoch += 1
+        counter = LaunchCounter()
+        ops.set_observer(counter)
+        engine.stage_inputs()
+        engine.device_iteration()
+        ops.set_observer(None)
+        if graphed:
+            engine.capture()
+            for _ in range(3):
+                engine.iteration(epoch)
+                epoch += 1
+        sampler = ClockSampler(local_rank) if sample_clocks and rank == 0 else None
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        swaps = 0
+        sync_all()
+        if sampler:
+            sampler.start()
+        for i in range(steps):
+            flush.zero_()                 # evict L2 between timed iterations (outside the per-step event pair)
+            engine.stage_inputs()         # device-to-device: next resident real batch into the step's input buffer
+            ev[i][0].record()
+            engine.device_iteration()     # graph replay (or eager launches with --no-graph)
+            if swap > 0 and engine.maybe_swap(epoch) is not None:   # server.py:315-333, worker.py:239-284
+                swaps += 1
+            ev[i][1].record()
+            epoch += 1
+        sync_all()
+        clocks = sampler.stop() if sampler else None
+        ms = max_over_ranks(sum(s_.elapsed_time(e_) for s_, e_ in ev)) / steps
+        return engine, mod, dataset, shards, {"ms_per_step": ms, "launches_per_step": counter.kernels, "swaps": swaps,
+                                               "clocks": clocks}
+
     # ---------------------------------------------------------------- device-resident leg (`value`)
-    engine = make_engine(resident=True, z_source="device")
-    for e in range(max(args.warmup, 3)):
-        engine.iteration(e)
-    counter = LaunchCounter()
-    ops.set_observer(counter)
-    engine.iteration(0)
-    ops.set_observer(None)
-    launches_per_step = counter.kernels
-    graphed = not args.no_graph
-    if graphed:
-        engine.capture()
-        for e in range(3):
-            engine.iteration(e)
-    sampler = ClockSampler(local_rank)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync_all()
-    if rank == 0:
-        sampler.start()
-    for i in range(args.steps):
-        flush.zero_()                 # evict L2 between timed iterations (outside the per-step event pair)
-        engine.stage_inputs()         # device-to-device: next resident real batch into the step's input buffer
-        ev[i][0].record()
-        engine.device_iteration()     # graph replay (or eager launches with --no-graph)
-        ev[i][1].record()
-    sync_all()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = max_over_ranks(sum(s.elapsed_time(e) for s, e in ev))
-    ms_per_step = ms_total / args.steps
+    engine, mod, dataset, shards, leg = device_leg(args.dataset, args.swap_interval, args.steps, args.warmup, True)
+    shape = tuple(mod.SHAPE)
+    ms_per_step, launches_per_step, clocks = leg["ms_per_step"], leg["launches_per_step"], leg["clocks"]
     gen_it_s = 1e3 / ms_per_step
     value = gen_it_s * n_workers
 
@@ -376,20 +443,19 @@ def run_ours(args) -> None:
     total_ms = sum(a["ms"] for a in per_op.values()) or 1.0
     top = max(per_op, key=lambda n: per_op[n]["ms"])
     a = per_op[top]
-    tensor_bound = top in ("conv_down", "conv_up", "conv_dense", "wgrad_gemm")
+    tensor_families = ("conv_down", "conv_up", "conv_dense", "wgrad_gemm")
+    tensor_bound = top in tensor_families
     traffic, traffic_note = None, None
-    tpath = REPO / "profiles" / "r01_traffic.json"
-    if tpath.exists() and args.dataset == "MNIST_DCGAN" and b == 64:
-        kname = "void wgrad_gemm_ta_kernel" if top == "wgrad_gemm" else ("void conv_gemm_ta_kernel" if tensor_bound else None)
-        rec = json.loads(tpath.read_text()).get("MNIST_DCGAN_b64_final_kernels", {}).get(kname)
+    tj = _profile_json("r02_traffic.json")
+    if tj:
+        rec = tj.get(f"{args.dataset}_b{b}", {}).get(top)
         if rec:
             traffic = rec["dram_bytes_per_launch_avg"]
-            traffic_note = ("ncu --set full capture of this workload (profiles/r01_traffic.json), cold caches, average "
-                            "over the launches of the kernel")
+            traffic_note = tj.get("how")
+    x3 = args.precision == "tf32x3"
     if tensor_bound:
         achieved = a["flops"] / (a["ms"] * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        x3 = args.precision == "tf32x3"
         ceiling = peak / (6.0 if x3 else 2.0)
         roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic,
@@ -408,6 +474,15 @@ def run_ours(args) -> None:
     roofline["avg_launch_us"] = a["ms"] * 1e3 / max(a["calls"], 1)
     roofline["launches_timed"] = a["calls"]
     roofline["share_of_step"] = a["ms"] / total_ms
+    # all tensor-core GEMMs of the step together: algorithmic FLOPs / their device time
+    t_ms = sum(per_op[n]["ms"] for n in tensor_families if n in per_op)
+    t_fl = sum(per_op[n]["flops"] for n in tensor_families if n in per_op)
+    if t_ms > 0:
+        roofline["all_gemms"] = {"achieved": t_fl / (t_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                 "frac": t_fl / (t_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+                                 "frac_of_mode_ceiling": t_fl / (t_ms * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] / (6.0 if x3 else 2.0)),
+                                 "share_of_step": t_ms / total_ms}
+    step_flops = sum(v["flops"] for v in per_op.values()) / 4
     engine.close()
     exchange_mode = getattr(engine.exchange, "mode", "nccl") if world > 1 else "none (one process)"
     shares = {n: {"share": round(v["ms"] / total_ms, 4), "us_per_iter": round(v["ms"] * 1e3 / 4, 2),
@@ -415,26 +490,30 @@ def run_ours(args) -> None:
     del engine
 
     # ---------------------------------------------------------------- end-to-end leg (host buffers in, losses out)
-    engine = make_engine(resident=False, z_source="host")
+    engine = make_engine(mod, dataset, shards, resident=False, z_source="host", swap=args.swap_interval)
     loss_host = torch.empty((len(local), 2), dtype=torch.float32, pin_memory=True)
-    for e in range(max(args.warmup, 3)):
-        engine.iteration(e)
+    epoch = 0
+    for _ in range(max(args.warmup, 3)):
+        engine.iteration(epoch)
+        epoch += 1
     if graphed:
         engine.capture()
-        for e in range(3):
-            engine.iteration(e)
+        for _ in range(3):
+            engine.iteration(epoch)
+            epoch += 1
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
     for i in range(args.steps):
         flush.zero_()
         ev2[i][0].record()
-        engine.iteration(i)                       # host RNG + pinned staging, H2D, the step (+ next step's host staging)
+        engine.iteration(epoch)                   # host RNG + pinned staging, H2D, the step (+ swap when due, + next step's host staging)
+        epoch += 1
         loss_host[:, 0].copy_(engine.d_loss[:, 0], non_blocking=True)   # D2H of the step's result
         loss_host[:, 1].copy_(engine.g_loss, non_blocking=True)
         ev2[i][1].record()
         ev2[i][1].synchronize()                   # the caller reads the losses every iteration (worker.py:215)
     sync_all()
-    e2e_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in ev2)) / args.steps
+    e2e_ms = max_over_ranks(sum(s_.elapsed_time(e_) for s_, e_ in ev2)) / args.steps
     img_bytes = 4 * b * shape[0] * shape[1] * shape[2]
     h2d = len(local) * img_bytes + (4 * engine.k * b * mod.Z_DIM if rank == 0 else 0)
     e2e = {"value": n_workers * 1e3 / e2e_ms, "unit": UNIT, "generator_it_s": 1e3 / e2e_ms, "ms_per_step": e2e_ms,
@@ -443,6 +522,21 @@ def run_ours(args) -> None:
                   "noise + host DataLoader batches -> pinned -> device, losses read back every iteration"}
     engine.close()
     del engine
+
+    # ---------------------------------------------------------------- per-shape sub-lines (device-timed step only)
+    shapes = {}
+    if not args.no_shapes:
+        sub_steps = min(args.steps, 20)
+        for ds_name, swap in (("MNIST_DCGAN", 0), ("CIFAR10", 1)):
+            if ds_name == args.dataset and swap == args.swap_interval:
+                continue
+            eng, _, _, _, sub = device_leg(ds_name, swap, sub_steps, 3, False)
+            eng.close()
+            del eng
+            shapes[f"{ds_name}_b{b}" + ("_swap1" if swap and n_workers > 1 else "")] = {
+                "workload": workload_name(args, n_workers, ds_name, swap), "ms_per_step": sub["ms_per_step"],
+                "generator_it_s": 1e3 / sub["ms_per_step"], "value": n_workers * 1e3 / sub["ms_per_step"], "unit": UNIT,
+                "steps": sub_steps, "swaps_in_timed_window": sub["swaps"], "gpu_launches_per_step": sub["launches_per_step"]}
 
     if world > 1:
         dist.barrier()
@@ -458,19 +552,24 @@ def run_ours(args) -> None:
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "tf32x3 (fp32-accurate)",
         "data": "synthetic",
+        # `config` names the workload and is identical in both arms; how OUR arm ran it is in `setup`
         "config": {"workload": workload_name(args, n_workers), "dataset": args.dataset, "batch": b, "workers": n_workers,
-                   "parallelism": f"one discriminator worker per GPU x{args.gpus}, generator on rank 0",
-                   "precision": args.precision, "cuda_graph": graphed, "exchange": exchange_mode,
-                   "l2": "512 MB buffer written between timed iterations (outside the per-step event pairs)",
-                   "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks"},
+                   "swap_interval": args.swap_interval},
+        "setup": {"parallelism": f"one discriminator worker per GPU x{args.gpus}, generator on rank 0",
+                  "precision": args.precision, "cuda_graph": graphed, "exchange": exchange_mode,
+                  "swaps_in_timed_window": leg["swaps"],
+                  "l2": "512 MB buffer written between timed iterations (outside the per-step event pairs)",
+                  "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
-        "tensor_pipe_util": {"source": "committed ncu --set full captures, profiles/r01_ncu_full_conv_wgrad.md (not measured "
-                                       "by this run: ncu numbers are never bench values)",
-                             "metric": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-                             "conv_128_wide_tiles_pct": [53, 75], "conv_64_wide_tiles_pct": [22, 30],
-                             "weight_gradient_pct": [22, 41]},
-        "gpu_launches_per_step": launches_per_step, "per_op": shares,
+        "gpu_launches_per_step": launches_per_step, "step_gflop_algorithmic_rank0": step_flops / 1e9,
+        "step_tflops_algorithmic_rank0": step_flops / (ms_per_step * 1e-3) / 1e12, "per_op": shares, "shapes": shapes,
     }
+    if selfcheck is not None:
+        line["multi_gpu_bit_identical"] = bool(selfcheck["ok"])
+        line["multi_gpu_check"] = selfcheck
+    tp = _profile_json("r02_tensor_pipe.json")
+    if tp:
+        line["tensor_pipe_util"] = tp
     emit(line)
     if world > 1:
         dist.destroy_process_group()

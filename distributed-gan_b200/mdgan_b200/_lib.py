@@ -23,7 +23,6 @@ SIGNATURES = {
     "mdgan_conv_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _f, _p]),
     "mdgan_wgrad_splits": (_i, [_i, _i, _i, _i, _i, _i]),
     "mdgan_wgrad_gemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "mdgan_debug_set_wgrad_desc": (None, [_i, _i]),
     "mdgan_pack_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_wgrad_unpack": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_pack_job_words": (_i, []),
@@ -41,7 +40,7 @@ SIGNATURES = {
     "mdgan_pad_rows": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mdgan_sum_slices": (_i, [_p, _p, _ll, _i, _ll, _p]),
     "mdgan_peer_signal": (_i, [_p, _i, _p, _i, _p]),
-    "mdgan_peer_wait": (_i, [_p, _i, _p, _i, _p, _p]),
+    "mdgan_peer_wait": (_i, [_p, _i, _p, _i, _p, _ll, _p]),
     "mdgan_peer_push": (_i, [_p, _p, _i, _ll, _p]),
     "mdgan_tanh_backward_slices": (_i, [_p, _p, _p, _ll, _i, _i, _f, _p]),
     "mdgan_thin_down": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p]),

@@ -99,7 +99,7 @@ bool pdl_enabled() {
 
 }  // namespace mdgan
 
-extern "C" int mdgan_abi_version(void) { return 1; }
+extern "C" int mdgan_abi_version(void) { return 2; }
 
 // Which SM architecture the loaded device code targets and whether the current device can run it.
 // Returns 0 when the current CUDA device is compute capability 10.x, MDGAN_ERR_UNSUPPORTED otherwise.

@@ -12,9 +12,13 @@
 // NHWC fp32 source on the fly (never materialised), B = packed weights [N_pad(*4 phases), taps*C] (K-major),
 // D[row, n] accumulates in TMEM.  Per CTA: 128 rows x BN columns, K stepped 32 fp32 (=128 B, one swizzle row)
 // at a time through a STAGES-deep smem ring.
-//   warps 0-7 : A producers (cp.async 16 B gathers with zero-fill for padding, manual 128B swizzle), then epilogue
-//   warp  8   : B producer (TMA 2D tiled load, SWIZZLE_128B, mbarrier complete_tx)
-//   warp  9   : TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees smem stages
+// Two kernels:
+//   conv_gemm_kernel    (single-pass tf32, and the tf32x3 predecessor MDGAN_CONV_TA=0): both operands in shared memory.
+//     warps 0-7 : A producers (global -> registers kPrefetch K steps ahead -> TF32 hi/lo split -> one swizzled
+//                 st.shared per operand), then the epilogue
+//     warp  8   : B producer (TMA 2D tiled load, SWIZZLE_128B, mbarrier complete_tx)
+//     warp  9   : TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees smem stages
+//   conv_gemm_ta_kernel (tf32x3 default): activation operand in tensor memory, see the comment above that kernel.
 //
 // Precision modes (template X3):
 //   tf32   : one tcgen05.mma per K=8 slice; operands are fp32 words that their producers rounded to TF32.
@@ -365,7 +369,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
 //   warps 0-3  : transposers: raw stage (row-wise, swizzle-aware LDS) -> hi/lo -> TMEM A stage
 //   warps 4-11 : loaders (global -> registers kPrefetch K steps ahead -> raw fp32 stage), then the epilogue
 //   warp  12   : B producer (TMA, hi + lo)        warp 13: TMEM allocator + single-thread MMA issuer
+//   warp  14   : (TMA_A only) activation-tile TMA issuer
+// With the TMA-fed activation tile the loader warps have nothing to load, so TG groups of four transposer warps
+// (warps 4g..4g+3, group g takes K steps g, g+TG, ...) work on consecutive K steps concurrently: one group's chain
+// (wait raw -> 8 LDS.128 -> split -> wait TMEM stage -> 2 tcgen05.st -> wait::st -> arrive) is ~1200 clk long and
+// was what paced a K step, not the tensor pipe (64-wide tiles: 552 clk of MMA per K step).
 constexpr int kTaThreads = (4 + kNumProducerWarps + 2) * 32;
+constexpr int kTaThreadsTma = kTaThreads + 32;
 
 template <int BN>
 struct ConvTaSmem {
@@ -397,8 +407,8 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // one tap x 32 channels, element strides = the conv stride, out-of-bounds = zero padding) instead of by the eight
 // loader warps: the tile then crosses the L1/shared-memory arrays once (the TMA write) instead of three times
 // (L1 fill, L1 read, shared store).  Possible whenever 128 consecutive rows of the (n, i, j) grid form a box.
-template <int BN, bool TMA_A>
-__global__ void __launch_bounds__(kTaThreads, 1)
+template <int BN, bool TMA_A, int TG>
+__global__ void __launch_bounds__(TMA_A ? kTaThreadsTma : kTaThreads, 1)
 conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
                     const ConvGemmParams p) {
   using S = ConvTaSmem<BN>;
@@ -432,7 +442,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     fence_mbar_init();
   }
   if (warp == 12 && lane == 0) tma_prefetch_desc(&tmap_w);
-  if (TMA_A && warp == 4 && lane == 0) tma_prefetch_desc(&tmap_a);
+  if (TMA_A && warp == 14 && lane == 0) tma_prefetch_desc(&tmap_a);
   if (warp == 13) tmem_alloc<S::kTmemCols>(tmem_ptr_smem);
   tc_fence_before_sync();
   __syncthreads();
@@ -440,127 +450,130 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ transposers: raw stage -> TMEM A stage
-    const int r = warp * 32 + lane;  // tile row == TMEM lane
-    const uint32_t row_base = smem_u32(smem) + r * 128;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + S::kACol0;
-    int s = 0, t = 0;
-    uint32_t pars = 0, part = 0;
-    for (int it = 0; it < ksteps; ++it) {
-      mbar_wait(&raw_full[s], pars);
-      float x[32];
+  static_assert(TG >= 1 && TG <= 3 && (TMA_A || TG == 1), "transposer groups: the loader warps double as transposers only when TMA feeds the tile");
+  if (warp < 12) {
+    if (warp < 4 * TG) {
+      // ---------------------------------------------------------------- transposers: raw stage -> TMEM A stage
+      const int r = (warp & 3) * 32 + lane;  // tile row == TMEM lane
+      const uint32_t row_base = smem_u32(smem) + r * 128;
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + S::kACol0;
+      for (int it = warp >> 2; it < ksteps; it += TG) {
+        const int s = it % S::kRawStages, t = it % S::kAStages;
+        const uint32_t pars = (it / S::kRawStages) & 1, part = (it / S::kAStages) & 1;
+        mbar_wait(&raw_full[s], pars);
+        float x[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = lds128(row_base + s * S::kRawBytes + ((c ^ (r & 7)) << 4));
-        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = lds128(row_base + s * S::kRawBytes + ((c ^ (r & 7)) << 4));
+          x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+        }
+        float hi[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) hi[j] = tf32_round_fast(x[j]);   // consumes every loaded word: the loads have landed
+        fence_proxy_async_smem();                    // order the generic-proxy reads before the next TMA write of the stage
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[s]);   // the row is in registers: the stage may be refilled
+        mbar_wait(&a_empty[t], part ^ 1);            // the MMAs that read this TMEM stage have completed
+        tc_fence_after_sync();
+        tmem_st_x32(t_lane + t * 64, hi);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] -= hi[j];  // lo = x - hi (exact); the tensor core truncates it to TF32
+        tmem_st_x32(t_lane + t * 64 + 32, x);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[t]);
       }
-      float hi[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) hi[j] = tf32_round_fast(x[j]);   // consumes every loaded word: the loads have landed
-      fence_proxy_async_smem();                    // order the generic-proxy reads before the next TMA write of the stage
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&raw_empty[s]);   // the row is in registers: the stage may be refilled
-      mbar_wait(&a_empty[t], part ^ 1);            // the MMAs that read this TMEM stage have completed
-      tc_fence_after_sync();
-      tmem_st_x32(t_lane + t * 64, hi);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] -= hi[j];  // lo = x - hi (exact); the tensor core truncates it to TF32
-      tmem_st_x32(t_lane + t * 64 + 32, x);
-      tmem_st_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[t]);
-      if (++s == S::kRawStages) { s = 0; pars ^= 1; }
-      if (++t == S::kAStages) { t = 0; part ^= 1; }
     }
-  } else if (warp < 4 + kNumProducerWarps) {
-    // ------------------------------------------------------------------ loaders (raw fp32 tile), then epilogue
-    if (TMA_A) {
-      if (warp == 4 && lane == 0) {
-        const int SIa = (p.mode == 0) ? 2 : 1;
-        const int n_start = m0 / (p.Hg * p.Wg);
-        const int h_start = (m0 - n_start * (p.Hg * p.Wg)) / p.Wg;
-        int s = 0, tap_l = 0, cc_l = 0;
-        uint32_t par = 0;
-        for (int it = 0; it < ksteps; ++it) {
+    if (warp >= 4) {
+      // ---------------------------------------------------------------- loaders (raw fp32 tile), then epilogue
+      if (!TMA_A) {
+        const int tid = threadIdx.x - 128;
+        const int chunk = tid & 7;
+        const int row_in = tid >> 3;  // 0..31
+        const int SI = (p.mode == 0) ? 2 : 1;
+        int base_off[4], sh0[4], sw0[4];
+        bool row_ok[4];
+        uint32_t soff[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = row_in + 32 * i;
+          const int m = m0 + r;
+          row_ok[i] = m < p.M;
+          const int mm = row_ok[i] ? m : 0;
+          const int img = mm / (p.Hg * p.Wg);
+          const int rem = mm - img * (p.Hg * p.Wg);
+          const int gi = rem / p.Wg, gj = rem - gi * p.Wg;
+          sh0[i] = gi * SI;
+          sw0[i] = gj * SI;
+          base_off[i] = ((img * p.Hs + sh0[i]) * p.Ws + sw0[i]) * p.C + chunk * 4;
+          soff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
+        }
+        const uint32_t raw0 = smem_u32(smem);
+        int tap_l = 0, cc_l = 0;
+        auto issue_loads = [&](float4(&buf)[4]) {
           int dh, dw;
           if (p.mode == 0) { dh = (tap_l >> 2) - 1; dw = (tap_l & 3) - 1; }
           else if (p.mode == 1) { dh = ph - (tap_l >> 1); dw = pw - (tap_l & 1); }
           else { dh = 0; dw = 0; }
-          mbar_wait(&raw_empty[s], par ^ 1);
-          mbar_arrive_expect_tx(&raw_full[s], p.rows_per_tile * 128);
-          tma_load_4d(smem_u32(smem) + s * S::kRawBytes, &tmap_a, &raw_full[s], cc_l * kBK, dw, h_start * SIa + dh, n_start);
+          const int tap_off = (dh * p.Ws + dw) * p.C + cc_l * kBK;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int sh = sh0[i] + dh, sw = sw0[i] + dw;
+            const bool ok = row_ok[i] && sh >= 0 && sh < p.Hs && sw >= 0 && sw < p.Ws;
+            buf[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.src + base_off[i] + tap_off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           if (++cc_l == cchunks) { cc_l = 0; ++tap_l; }
-          if (++s == S::kRawStages) { s = 0; par ^= 1; }
+        };
+        float4 buf[kPrefetch][4];
+#pragma unroll
+        for (int u = 0; u < kPrefetch; ++u)
+          if (u < ksteps) issue_loads(buf[u]);
+        int s = 0;
+        uint32_t par = 0;
+        for (int it0 = 0; it0 < ksteps; it0 += kPrefetch) {
+#pragma unroll
+          for (int u = 0; u < kPrefetch; ++u) {
+            const int it = it0 + u;
+            if (it < ksteps) {
+              mbar_wait(&raw_empty[s], par ^ 1);
+              const uint32_t stage = raw0 + s * S::kRawBytes;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) sts128(stage + soff[i], buf[u][i].x, buf[u][i].y, buf[u][i].z, buf[u][i].w);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&raw_full[s]);
+              if (it + kPrefetch < ksteps) issue_loads(buf[u]);
+              if (++s == S::kRawStages) { s = 0; par ^= 1; }
+            }
+          }
         }
       }
-    } else {
-      const int tid = threadIdx.x - 128;
-      const int chunk = tid & 7;
-      const int row_in = tid >> 3;  // 0..31
-      const int SI = (p.mode == 0) ? 2 : 1;
-      int base_off[4], sh0[4], sw0[4];
-      bool row_ok[4];
-      uint32_t soff[4];
-  #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = row_in + 32 * i;
-        const int m = m0 + r;
-        row_ok[i] = m < p.M;
-        const int mm = row_ok[i] ? m : 0;
-        const int img = mm / (p.Hg * p.Wg);
-        const int rem = mm - img * (p.Hg * p.Wg);
-        const int gi = rem / p.Wg, gj = rem - gi * p.Wg;
-        sh0[i] = gi * SI;
-        sw0[i] = gj * SI;
-        base_off[i] = ((img * p.Hs + sh0[i]) * p.Ws + sw0[i]) * p.C + chunk * 4;
-        soff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
-      }
-      const uint32_t raw0 = smem_u32(smem);
-      int tap_l = 0, cc_l = 0;
-      auto issue_loads = [&](float4(&buf)[4]) {
+      __syncwarp();
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after_sync();
+      conv_epilogue<BN, S::kAccs>(p, tmem_base, warp & 3, (warp - 4) >> 2, lane, m0, n0, ph, pw);
+      tc_fence_before_sync();
+    }
+  } else if (TMA_A && warp == 14) {
+    // ------------------------------------------------------------------ activation tile producer (TMA, 4-D box)
+    if (lane == 0) {
+      const int SIa = (p.mode == 0) ? 2 : 1;
+      const int n_start = m0 / (p.Hg * p.Wg);
+      const int h_start = (m0 - n_start * (p.Hg * p.Wg)) / p.Wg;
+      int s = 0, tap_l = 0, cc_l = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < ksteps; ++it) {
         int dh, dw;
         if (p.mode == 0) { dh = (tap_l >> 2) - 1; dw = (tap_l & 3) - 1; }
         else if (p.mode == 1) { dh = ph - (tap_l >> 1); dw = pw - (tap_l & 1); }
         else { dh = 0; dw = 0; }
-        const int tap_off = (dh * p.Ws + dw) * p.C + cc_l * kBK;
-  #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int sh = sh0[i] + dh, sw = sw0[i] + dw;
-          const bool ok = row_ok[i] && sh >= 0 && sh < p.Hs && sw >= 0 && sw < p.Ws;
-          buf[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.src + base_off[i] + tap_off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        mbar_wait(&raw_empty[s], par ^ 1);
+        mbar_arrive_expect_tx(&raw_full[s], p.rows_per_tile * 128);
+        tma_load_4d(smem_u32(smem) + s * S::kRawBytes, &tmap_a, &raw_full[s], cc_l * kBK, dw, h_start * SIa + dh, n_start);
         if (++cc_l == cchunks) { cc_l = 0; ++tap_l; }
-      };
-      float4 buf[kPrefetch][4];
-  #pragma unroll
-      for (int u = 0; u < kPrefetch; ++u)
-        if (u < ksteps) issue_loads(buf[u]);
-      int s = 0;
-      uint32_t par = 0;
-      for (int it0 = 0; it0 < ksteps; it0 += kPrefetch) {
-  #pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) {
-          const int it = it0 + u;
-          if (it < ksteps) {
-            mbar_wait(&raw_empty[s], par ^ 1);
-            const uint32_t stage = raw0 + s * S::kRawBytes;
-  #pragma unroll
-            for (int i = 0; i < 4; ++i) sts128(stage + soff[i], buf[u][i].x, buf[u][i].y, buf[u][i].z, buf[u][i].w);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_full[s]);
-            if (it + kPrefetch < ksteps) issue_loads(buf[u]);
-            if (++s == S::kRawStages) { s = 0; par ^= 1; }
-          }
-        }
+        if (++s == S::kRawStages) { s = 0; par ^= 1; }
       }
     }
-    __syncwarp();  // warp 4's lane 0 was issuing TMA loads: converge before the warp-aligned tcgen05.ld below
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after_sync();
-    conv_epilogue<BN, S::kAccs>(p, tmem_base, warp & 3, (warp - 4) >> 2, lane, m0, n0, ph, pw);
-    tc_fence_before_sync();
   } else if (warp == 12) {
     // ------------------------------------------------------------------ B producer (TMA, hi + lo)
     if (lane == 0) {
@@ -576,7 +589,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         if (++s == S::kBStages) { s = 0; par ^= 1; }
       }
     }
-  } else {
+  } else if (warp == 13) {
     // ------------------------------------------------------------------ MMA issuer (A from TMEM, B from shared memory)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
@@ -617,19 +630,35 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   }
 }
 
-template <int BN, bool TMA_A>
+template <int BN, bool TMA_A, int TG>
 static int launch_conv_gemm_ta(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p, dim3 grid,
                                cudaStream_t st) {
   using S = ConvTaSmem<BN>;
   static_assert(S::kDynamic <= 227 * 1024, "shared memory per CTA");
-  static bool configured = false;
-  if (!configured) {
-    MDGAN_CUDA(cudaFuncSetAttribute(conv_gemm_ta_kernel<BN, TMA_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    S::kDynamic));
-    configured = true;
-  }
-  MDGAN_LAUNCH((conv_gemm_ta_kernel<BN, TMA_A>), grid, dim3(kTaThreads), S::kDynamic, st, tmap, tmap_a, p);
+  MDGAN_CUDA(configure_smem_once(conv_gemm_ta_kernel<BN, TMA_A, TG>, S::kDynamic));
+  MDGAN_LAUNCH((conv_gemm_ta_kernel<BN, TMA_A, TG>), grid, dim3(TMA_A ? kTaThreadsTma : kTaThreads), S::kDynamic, st, tmap,
+               tmap_a, p);
   return 0;
+}
+
+// MDGAN_CONV_TG = 1 | 2 | 3 (default 2): groups of transposer warps of the TMA-fed kernel (see conv_gemm_ta_kernel).
+static int conv_tg() {
+  static const int tg = [] {
+    const char* e = getenv("MDGAN_CONV_TG");
+    const int v = e ? atoi(e) : 2;
+    return v < 1 ? 1 : (v > 3 ? 3 : v);
+  }();
+  return tg;
+}
+
+template <int BN>
+static int launch_conv_gemm_ta_tma(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p, dim3 grid,
+                                   cudaStream_t st) {
+  switch (conv_tg()) {
+    case 1: return launch_conv_gemm_ta<BN, true, 1>(tmap, tmap_a, p, grid, st);
+    case 2: return launch_conv_gemm_ta<BN, true, 2>(tmap, tmap_a, p, grid, st);
+    default: return launch_conv_gemm_ta<BN, true, 3>(tmap, tmap_a, p, grid, st);
+  }
 }
 
 // MDGAN_CONV_TMA_PARTIAL = 1 (default) | 0: also use TMA boxes of whole images that do not fill 128 rows (7x7 grids).
@@ -663,12 +692,7 @@ template <int BN, int STAGES, bool X3>
 static int launch_conv_gemm(const CUtensorMap& tmap, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
   using S = ConvGemmSmem<BN, STAGES, X3>;
   static_assert(S::kDynamic <= 227 * 1024, "shared memory per CTA");
-  static bool configured = false;
-  if (!configured) {
-    MDGAN_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    S::kDynamic));
-    configured = true;
-  }
+  MDGAN_CUDA(configure_smem_once(conv_gemm_kernel<BN, STAGES, X3>, S::kDynamic));
   MDGAN_LAUNCH((conv_gemm_kernel<BN, STAGES, X3>), grid, dim3(kThreads), S::kDynamic, st, tmap, p);
   return 0;
 }
@@ -750,18 +774,18 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
     }
     if (tma_a) {
       switch (bn) {
-        case 128: return launch_conv_gemm_ta<128, true>(tmap, tmap_a, p, grid, st);
-        case 64: return launch_conv_gemm_ta<64, true>(tmap, tmap_a, p, grid, st);
-        case 32: return launch_conv_gemm_ta<32, true>(tmap, tmap_a, p, grid, st);
-        case 16: return launch_conv_gemm_ta<16, true>(tmap, tmap_a, p, grid, st);
+        case 128: return launch_conv_gemm_ta_tma<128>(tmap, tmap_a, p, grid, st);
+        case 64: return launch_conv_gemm_ta_tma<64>(tmap, tmap_a, p, grid, st);
+        case 32: return launch_conv_gemm_ta_tma<32>(tmap, tmap_a, p, grid, st);
+        case 16: return launch_conv_gemm_ta_tma<16>(tmap, tmap_a, p, grid, st);
         default: return MDGAN_ERR_UNSUPPORTED;
       }
     }
     switch (bn) {
-      case 128: return launch_conv_gemm_ta<128, false>(tmap, tmap_a, p, grid, st);
-      case 64: return launch_conv_gemm_ta<64, false>(tmap, tmap_a, p, grid, st);
-      case 32: return launch_conv_gemm_ta<32, false>(tmap, tmap_a, p, grid, st);
-      case 16: return launch_conv_gemm_ta<16, false>(tmap, tmap_a, p, grid, st);
+      case 128: return launch_conv_gemm_ta<128, false, 1>(tmap, tmap_a, p, grid, st);
+      case 64: return launch_conv_gemm_ta<64, false, 1>(tmap, tmap_a, p, grid, st);
+      case 32: return launch_conv_gemm_ta<32, false, 1>(tmap, tmap_a, p, grid, st);
+      case 16: return launch_conv_gemm_ta<16, false, 1>(tmap, tmap_a, p, grid, st);
       default: return MDGAN_ERR_UNSUPPORTED;
     }
   }

@@ -30,19 +30,30 @@ __global__ void peer_signal_kernel(const unsigned long long* __restrict__ flag_a
   if (advance && threadIdx.x == 0) *epoch = target;
 }
 
-// spin until every flags[i] (local memory, written by peers) >= *epoch + 1.  err[0] is set (and the wait abandoned)
-// after ~30 s without progress so that a dead peer surfaces as an error instead of a hung GPU.
-__global__ void peer_wait_kernel(const int* __restrict__ flags, int n, int* epoch, int advance, int* err) {
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// spin until every flags[i] (local memory, written by peers) >= *epoch + 1.  A flag that does not arrive within
+// timeout_ns of WALL time (globaltimer) means a peer process died: err[0] is set and the kernel TRAPS -- the context is
+// lost and every later call of this process fails loudly, instead of the rest of the captured iteration consuming a
+// stale generated batch / feedback and corrupting the discriminator or generator state.
+__global__ void peer_wait_kernel(const int* __restrict__ flags, int n, int* epoch, int advance, int* err,
+                                 unsigned long long timeout_ns) {
   pdl_enter();
   const int target = *reinterpret_cast<volatile int*>(epoch) + 1;
   if ((int)threadIdx.x < n) {
     const int* f = flags + threadIdx.x;
-    long long spins = 0;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
     while (ld_acquire_sys(f) < target) {
-      __nanosleep(64);
-      if (++spins > (1LL << 24)) {
+      __nanosleep(spins < 64 ? 32 : 256);   // a healthy exchange answers within microseconds: poll fast first
+      if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
         atomicExch(err, 1);
-        break;
+        __threadfence_system();
+        __trap();
       }
     }
   }
@@ -98,9 +109,11 @@ extern "C" int mdgan_peer_signal(const unsigned long long* flag_addrs_dev, int n
   return 0;
 }
 
-extern "C" int mdgan_peer_wait(const int* flags, int n, int* epoch, int advance, int* err, void* stream) {
-  if (!flags || !epoch || !err || n < 0 || n > 64) return MDGAN_ERR_BAD_ARG;
-  MDGAN_LAUNCH(peer_wait_kernel, dim3(1), dim3(64), 0, (cudaStream_t)stream, flags, n, epoch, advance, err);
+extern "C" int mdgan_peer_wait(const int* flags, int n, int* epoch, int advance, int* err, long long timeout_ms,
+                               void* stream) {
+  if (!flags || !epoch || !err || n < 0 || n > 64 || timeout_ms <= 0) return MDGAN_ERR_BAD_ARG;
+  MDGAN_LAUNCH(peer_wait_kernel, dim3(1), dim3(64), 0, (cudaStream_t)stream, flags, n, epoch, advance, err,
+               static_cast<unsigned long long>(timeout_ms) * 1000000ULL);
   return 0;
 }
 

@@ -361,11 +361,7 @@ extern "C" int mdgan_thin_up(const float* src, const float* W, float* out, int n
   const size_t smem = (size_t)C * (N * 16 + 4) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 3) {
-    static bool configured = false;
-    if (!configured) {
-      MDGAN_CUDA(cudaFuncSetAttribute(thin_up_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 52 * 4));
-      configured = true;
-    }
+    MDGAN_CUDA(configure_smem_once(thin_up_kernel<3>, 256 * 52 * 4));
     MDGAN_LAUNCH(thin_up_kernel<3>, dim3(blocks), dim3(256), smem, st, src, W, out, n_img, H, Wd, C, act_tanh, accumulate);
   } else {
     MDGAN_LAUNCH(thin_up_kernel<1>, dim3(blocks), dim3(256), smem, st, src, W, out, n_img, H, Wd, C, act_tanh, accumulate);

@@ -529,11 +529,7 @@ template <int BN>
 static int launch_wgrad_ta(const CUtensorMap& tmap_lo, const WgradParams& p, dim3 grid, cudaStream_t st) {
   using S = WgradTaSmem<BN>;
   static_assert(S::kDynamic <= 227 * 1024, "shared memory per CTA");
-  static bool configured = false;
-  if (!configured) {
-    MDGAN_CUDA(cudaFuncSetAttribute(wgrad_gemm_ta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
-    configured = true;
-  }
+  MDGAN_CUDA(configure_smem_once(wgrad_gemm_ta_kernel<BN>, S::kDynamic));
   MDGAN_LAUNCH((wgrad_gemm_ta_kernel<BN>), grid, dim3(kWTaThreads), S::kDynamic, st, tmap_lo, p);
   return 0;
 }
@@ -551,19 +547,10 @@ template <int BN, int STAGES, bool X3>
 static int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
   using S = WgradSmem<BN, STAGES, X3>;
   static_assert(S::kDynamic <= 227 * 1024, "shared memory per CTA");
-  static bool configured = false;
-  if (!configured) {
-    MDGAN_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BN, STAGES, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    S::kDynamic));
-    configured = true;
-  }
+  MDGAN_CUDA(configure_smem_once(wgrad_gemm_kernel<BN, STAGES, X3>, S::kDynamic));
   MDGAN_LAUNCH((wgrad_gemm_kernel<BN, STAGES, X3>), grid, dim3(kWThreads), S::kDynamic, st, p);
   return 0;
 }
-
-// Debug override of the MN-major descriptor offsets (0 = use defaults); used once on hardware to confirm the
-// encoding, kept as a C-ABI knob for the parity tests.
-static int g_dbg_lbo = 0, g_dbg_sbo = 0;
 
 // Tile width of mdgan_wgrad_gemm for a given C2 (both precisions): 128 when it divides C2, else 64.
 static int wgrad_bn(int C2) { return C2 % 128 == 0 ? 128 : 64; }
@@ -571,11 +558,6 @@ static int wgrad_bn(int C2) { return C2 % 128 == 0 ? 128 : 64; }
 }  // namespace mdgan
 
 using namespace mdgan;
-
-extern "C" void mdgan_debug_set_wgrad_desc(int lbo_bytes, int sbo_bytes) {
-  g_dbg_lbo = lbo_bytes;
-  g_dbg_sbo = sbo_bytes;
-}
 
 // Number of split-K partial slices mdgan_wgrad_gemm will write for this problem (the caller sizes `partial`
 // as splits * taps * C1 * C2 floats).
@@ -607,8 +589,8 @@ extern "C" int mdgan_wgrad_gemm(const float* lo, const float* hi, float* partial
   if (p.P >= (1 << 28) / (Hl * Wl > 0 ? 1 : 1) && static_cast<long long>(p.P) * Hl * Wl >= (1LL << 40)) return MDGAN_ERR_UNSUPPORTED;
   p.magic_hw = ((1ULL << 40) + static_cast<unsigned long long>(Hl * Wl) - 1) / static_cast<unsigned long long>(Hl * Wl);
   p.magic_w = ((1ULL << 40) + static_cast<unsigned long long>(Wl) - 1) / static_cast<unsigned long long>(Wl);
-  p.lbo_a = p.lbo_b = g_dbg_lbo ? g_dbg_lbo : kWK * 128;  // distance between 32-channel groups
-  p.sbo_a = p.sbo_b = g_dbg_sbo ? g_dbg_sbo : 512;        // distance between 4-pixel swizzle atoms
+  p.lbo_a = p.lbo_b = kWK * 128;  // distance between 32-channel groups (encoding confirmed on hardware, round 1)
+  p.sbo_a = p.sbo_b = 512;        // distance between 4-pixel swizzle atoms
   const int taps = mode == 0 ? 16 : 1;
   const int bn = wgrad_bn(C2);
   dim3 grid(C1 / kWM, C2 / bn, taps * splits);

@@ -217,25 +217,47 @@ class MDGANEngine:
         self.train_workers()
         self.update_generator()
 
-    def device_iteration(self) -> None:
-        """Device half of an iteration: uploads (eager) + the compute part (the captured graph if there is one)."""
-        self.upload_inputs()
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self.compute_iteration()
+    def _phases(self):
+        return (lambda: self.generate(staged=True), self.train_workers, self.update_generator)
 
-    def capture(self) -> None:
+    def device_iteration(self, marks=None) -> None:
+        """Device half of an iteration: uploads (eager) + the compute part (the captured graph(s) if there are any).
+        marks: optional list of three CUDA events recorded on the compute stream after the generate / train-workers /
+        update-generator phases (needs eager launches or `capture(split=True)`): the device-time spans of the
+        reference's CSV columns (server.py:179-208)."""
+        self.upload_inputs()
+        if self.graph is None or isinstance(self.graph, list):
+            for i, phase in enumerate(self.graph if self.graph is not None else self._phases()):
+                phase.replay() if self.graph is not None else phase()
+                if marks is not None:
+                    marks[i].record()
+        else:
+            if marks is not None:
+                raise RuntimeError("phase marks need eager launches or capture(split=True)")
+            self.graph.replay()
+
+    def capture(self, split: bool = False) -> None:
         """Capture the device half of the steady-state iteration into one CUDA graph (at b <= 128 the
-        iteration is launch-bound).  Call after at least one eager iteration (lazy kernel attributes, tensor maps
-        and NCCL communicators must exist).  The swap stays outside the graph: it is host-driven and rare."""
+        iteration is launch-bound) -- or, split=True, into three (generate + broadcast / D steps + feedback + reduce /
+        G backward + Adam) replayed back to back so that CUDA events can mark the phase boundaries.  Call after at
+        least one eager iteration (lazy kernel attributes, tensor maps and NCCL communicators must exist).  The swap
+        stays outside the graph: it is host-driven and rare."""
         if self.device.type != "cuda":
             raise RuntimeError("CUDA graphs need a CUDA device")
         torch.cuda.synchronize(self.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self.compute_iteration()
-        self.graph = graph
+        if not split:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.compute_iteration()
+            self.graph = graph
+            return
+        graphs = []
+        for phase in self._phases():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=graphs[0].pool() if graphs else None):
+                phase()
+            graphs.append(g)
+        self.graph = graphs
 
     def close(self) -> None:
         """Release the captured graph.  Must happen before the process group is destroyed: tearing down an NCCL

@@ -175,7 +175,7 @@ class _SnapshotWriter:
 
 
 def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: torch.device, cfg: EngineConfig,
-             generator: Optional[nn.Module], discriminators: Dict[int, nn.Module], dataset, get_subset=None,
+             generator: Optional[nn.Module], discriminators: Dict[int, nn.Module], dataset,
              epochs: int, log_interval: int, log_folder: Path, dataset_name: str, iid: bool = True, n_samples: int = 5,
              engine_hook=None) -> MDGANEngine:
     N = routing.num_workers(world_size)
@@ -233,56 +233,59 @@ def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: 
         model_mb[n] = (sum(p.nelement() * p.element_size() for p in m.parameters())
                        + sum(bf.nelement() * bf.element_size() for bf in m.buffers())) / _MB
 
-    sync_timing = os.environ.get("MDGAN_SYNC_TIMING", "0") == "1"
-
-    def stamp() -> float:
-        if sync_timing:
-            torch.cuda.synchronize(device)
-        return time.time()
-
-    # Steady state runs as one CUDA graph per iteration (captured after two eager iterations); MDGAN_GRAPH=0 or
-    # MDGAN_SYNC_TIMING=1 (per-phase device-synchronised CSV spans) keep the eager phase-by-phase launches.
-    use_graph = os.environ.get("MDGAN_GRAPH", "1") == "1" and not sync_timing
+    # CSV spans are DEVICE times: CUDA events on the compute stream mark the phase boundaries (start of the iteration,
+    # after generate+broadcast, after the D steps+feedback+reduce, after G backward+Adam, after the swap) and are
+    # converted to wall-clock seconds through one (host time, event) anchor pair; the row of an iteration is written
+    # after its loss read-back, which synchronises anyway.  Steady state runs as three CUDA graphs replayed back to
+    # back (captured after two eager iterations) so the marks survive graph replay; MDGAN_GRAPH=0 keeps eager launches.
+    use_graph = os.environ.get("MDGAN_GRAPH", "1") == "1"
     FID, IS = _maybe_metrics()
+    if FID is None and proc == 0:
+        logging.warning("torchmetrics is not importable: the fid / is columns of the server CSV stay empty "
+                        "(the reference requires torchmetrics, /root/reference/src/actors/server.py:16-17)")
     snapshots = _SnapshotWriter(device) if (proc == 0 and FID is None) else None
+    torch.cuda.synchronize(device)
+    anchor = torch.cuda.Event(enable_timing=True)
+    anchor.record()
+    anchor.synchronize()
+    anchor_t = time.time()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def at(ev) -> float:
+        return anchor_t + anchor.elapsed_time(ev) * 1e-3
+
     for epoch in range(epochs):
         if use_graph and epoch == 2:
-            engine.capture()
-        t0 = stamp()
+            engine.capture(split=True)
+        h0 = time.time()
+        engine.stage_inputs()                 # host: noise draw in the reference's RNG order, loader batches -> pinned
+        marks[0].record()
+        engine.device_iteration(marks[1:4])   # uploads + generate / D steps + feedback / G backward + Adam
+        engine.prefetch_next(epoch, last=(epoch == epochs - 1))  # next iteration's host inputs while the GPU works
+        pairs = engine.maybe_swap(epoch)
+        marks[4].record()
+        engine.iterations_done += 1
+        losses = engine.mean_d_loss()  # one small D2H per iteration, like the reference's losses.mean().item()
+        marks[4].synchronize()
+        t0, t1, t2, t3, t4 = (at(m) for m in marks)
         srow = {c: None for c in SERVER_COLUMNS}
-        srow.update({"epoch": epoch, "start.epoch": t0, "start.epoch_calculation": t0, "swap": False,
+        srow.update({"epoch": epoch, "start.epoch": h0, "start.epoch_calculation": t0, "swap": False,
                      "size.data": 2 * img_bytes / _MB, "size.feedback": N * img_bytes / _MB,
-                     "size.sent": N * 2 * img_bytes / _MB, "size.recv": N * img_bytes / _MB})
+                     "size.sent": N * 2 * img_bytes / _MB, "size.recv": N * img_bytes / _MB,
+                     "start.generate_data": t0, "end.generate_data": t1,
+                     # the batch leaves inside the generate phase (peer stores / broadcast are its last kernels)
+                     "start.send_data": t1, "end.send_data": t1,
+                     # waiting for the workers = their D steps + feedback (+ the reduce / flag wait)
+                     "start.recv_data": t1, "end.recv_data": t2,
+                     # aggregation = the ONE generator backward on the group-summed feedback, fused with Adam
+                     "start.agg_gradients": t2, "end.agg_gradients": t3,
+                     "start.calc_gradients": t2, "end.calc_gradients": t3, "end.epoch_calculation": t4})
         wrows = {n: {c: None for c in WORKER_COLUMNS} for n in local}
         for n in local:
-            wrows[n].update({"epoch": epoch, "start.epoch": t0, "size.model": model_mb[n],
-                             "size.sent": img_bytes / _MB, "size.recv": 2 * img_bytes / _MB})
-        srow["start.generate_data"] = t0
-        if engine.graph is None:
-            engine.generate()
-            t1 = stamp()
-        else:
-            engine.stage_inputs()
-            t1 = stamp()
-        srow["end.generate_data"] = srow["start.send_data"] = srow["end.send_data"] = srow["start.recv_data"] = t1
-        for n in local:
-            wrows[n]["start.recv_data"], wrows[n]["end.recv_data"], wrows[n]["start.calc_gradients"] = t0, t1, t1
-        if engine.graph is None:
-            engine.train_workers()
-        else:
-            engine.device_iteration()   # uploads + the captured G forward / D steps / feedback / G backward / Adam
-            engine.prefetch_next(epoch, last=(epoch == epochs - 1))  # next iteration's host inputs while the GPU works
-        t2 = stamp()
-        srow["end.recv_data"] = srow["start.agg_gradients"] = t2
-        for n in local:
-            wrows[n]["end.calc_gradients"] = wrows[n]["start.send"] = wrows[n]["end.send"] = wrows[n]["end.epoch"] = t2
-        if engine.graph is None:
-            engine.update_generator()
-        t3 = stamp()
-        srow["end.agg_gradients"] = srow["start.calc_gradients"] = srow["end.calc_gradients"] = t3
-        pairs = engine.maybe_swap(epoch)
-        engine.iterations_done += 1
-        t4 = stamp()
+            wrows[n].update({"epoch": epoch, "start.epoch": h0, "size.model": model_mb[n],
+                             "size.sent": img_bytes / _MB, "size.recv": 2 * img_bytes / _MB,
+                             "start.recv_data": t0, "end.recv_data": t1, "start.calc_gradients": t1,
+                             "end.calc_gradients": t2, "start.send": t2, "end.send": t2, "end.epoch": t4})
         if pairs is not None:
             srow.update({"swap": True, "start.swap": t3, "end.swap": t4})
             for n in local:
@@ -292,15 +295,14 @@ def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: 
                                  "end.load_state_dict": t4})
                 wrows[n]["size.sent"] += model_mb[n]
                 wrows[n]["size.recv"] += model_mb[n]
-        srow["end.epoch_calculation"] = t4
-        losses = engine.mean_d_loss()  # one small D2H per iteration, like the reference's losses.mean().item()
         for i, n in enumerate(local):
             wrows[n]["mean_d_loss"] = losses[i]
             worker_writers[n].writerow(wrows[n])
+        log_now = epoch % log_interval == 0 or epoch == epochs - 1
         if proc == 0:
-            if (epoch % log_interval == 0 or epoch == epochs - 1) and snapshots is not None:  # server.py:336-367
+            if log_now and snapshots is not None:  # server.py:336-367
                 snapshots.submit(engine, image_dir / f"generated_epoch_{epoch}.png", weights_dir / f"generator_{epoch}.pt")
-            elif epoch % log_interval == 0 or epoch == epochs - 1:  # with torchmetrics: FID / IS need the images now
+            elif log_now:  # with torchmetrics: FID / IS need the images now
                 fake = engine.X.detach().cpu()
                 fake = fake.repeat(1, 3, 1, 1) if fake.shape[1] < 3 else fake
                 fake = (fake + 1) * 0.5
@@ -322,6 +324,10 @@ def run_node(*, backend: str, proc: int, n_procs: int, world_size: int, device: 
                 torch.save(generator.state_dict(), weights_dir / f"generator_{epoch}.pt")
             srow["end.epoch"] = time.time()
             server_w.writerow(srow)
+        if log_now and FID is not None and n_procs > 1:
+            # the synchronous evaluation above can take minutes on process 0: hold the other processes on the HOST
+            # here instead of letting them replay the next iteration and spin in a flag wait on the device
+            dist.barrier(group=engine.exchange.ctl_group)
 
     torch.cuda.synchronize(device)
     if snapshots is not None:

@@ -365,9 +365,15 @@ def peer_signal(flag_addrs: torch.Tensor, n: int, epoch: torch.Tensor, advance: 
          lambda: _lib.load().mdgan_peer_signal(_ptr(flag_addrs), n, _ptr(epoch), int(advance), _stream()))
 
 
+def peer_timeout_ms() -> int:
+    """MDGAN_PEER_TIMEOUT_S (default 600): wall time a flag wait may last before the kernel traps (dead peer)."""
+    return max(1, int(float(os.environ.get("MDGAN_PEER_TIMEOUT_S", "600")) * 1000))
+
+
 def peer_wait(flags: torch.Tensor, n: int, epoch: torch.Tensor, advance: bool, err: torch.Tensor):
     _run("peer_wait", 1, 0, 4.0 * n,
-         lambda: _lib.load().mdgan_peer_wait(_ptr(flags), n, _ptr(epoch), int(advance), _ptr(err), _stream()))
+         lambda: _lib.load().mdgan_peer_wait(_ptr(flags), n, _ptr(epoch), int(advance), _ptr(err),
+                                             C.c_longlong(peer_timeout_ms()), _stream()))
 
 
 def peer_push(src: torch.Tensor, dst_addrs: torch.Tensor, n_dst: int):

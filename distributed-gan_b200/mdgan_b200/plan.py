@@ -231,8 +231,10 @@ def _validate(plan: NetPlan) -> None:
         if L[-1].bias is not None:
             raise UnsupportedModelError("generator output layer must not have a bias")
     else:
-        if any(l.kind != "down" for l in L[:-1]) or L[-1].kind != "head" or len(L) < 2:
-            raise UnsupportedModelError("discriminator must be Conv(4,2,1) layers followed by a kxk valid-conv head")
+        # >= 3 layers: the LeakyReLU backward of layer 0 is the fused epilogue of layer 1's data-gradient GEMM
+        # (DiscNet.backward), so a Conv -> head model has no kernel that would write dz[0]
+        if any(l.kind != "down" for l in L[:-1]) or L[-1].kind != "head" or len(L) < 3:
+            raise UnsupportedModelError("discriminator must be >= 2 Conv(4,2,1) layers followed by a kxk valid-conv head")
         if L[0].bn is not None or L[0].act != ACT_LRELU or L[0].bias is not None or L[0].c_in not in (1, 3):
             raise UnsupportedModelError("first discriminator layer must be Conv(bias=False) -> LeakyReLU on 1/3 channels")
         for l in L[1:-1]:

@@ -91,7 +91,6 @@ int mdgan_wgrad_gemm(const float* lo, const float* hi, float* partial, int n_img
 int mdgan_wgrad_unpack(const float* partial, float* grad, int mode, int splits, int C1, int C1p, int C2, int N, int KK,
                        void* stream);
 int mdgan_reduce_slices(const float* partial, float* out, int slices, long long n, void* stream);
-void mdgan_debug_set_wgrad_desc(int lbo_bytes, int sbo_bytes);
 
 /* ---- image-side ("thin", 1 or 3 channel) layers on CUDA cores -------------------------------------------------
  * mdgan_thin_down : img NCHW [n][CI][Hi][Wi], W [N][CI][4][4] -> out NHWC [n][Hi/2][Wi/2][N] (+ LeakyReLU).
@@ -165,13 +164,15 @@ int mdgan_sum_slices(const float* in, float* out, long long n, int count, long l
  *   mdgan_peer_signal: *(int*)flag_addrs_dev[i] = *epoch + 1 for i < n (peer-mapped addresses, release at system
  *     scope after a system fence); advance = 1 also stores *epoch + 1 to *epoch.
  *   mdgan_peer_wait  : spins until flags[i] >= *epoch + 1 for i < n (local memory written by peers, acquire at
- *     system scope); advance as above; *err = 1 if a flag does not arrive within ~30 s (the wait is then abandoned).
+ *     system scope); advance as above.  A flag that does not arrive within timeout_ms of wall time (a peer process
+ *     died) sets *err = 1 and TRAPS the kernel: the context is lost and later calls fail, rather than the rest of
+ *     the iteration running on stale data.
  *   mdgan_peer_push  : dst_j[0..n) = src[0..n) for the n_dst peer-mapped destinations dst_addrs_dev[j] (n % 4 == 0).
  *   mdgan_tanh_backward_slices: out[s][j] = scale * (1 - x[s][j]^2) * sum_{w = s, s+k, .. < N} F[w][j], j < n_per_slot:
  *     the feedbacks of the workers sharing generated batch s, summed in ascending worker order, fused with the
  *     generator's tanh backward (F: [N][n_per_slot] slices written by the workers' feedback kernels). */
 int mdgan_peer_signal(const unsigned long long* flag_addrs_dev, int n, int* epoch, int advance, void* stream);
-int mdgan_peer_wait(const int* flags, int n, int* epoch, int advance, int* err, void* stream);
+int mdgan_peer_wait(const int* flags, int n, int* epoch, int advance, int* err, long long timeout_ms, void* stream);
 int mdgan_peer_push(const float* src, const unsigned long long* dst_addrs_dev, int n_dst, long long n, void* stream);
 int mdgan_tanh_backward_slices(const float* F, const float* x, float* out, long long n_per_slot, int k, int N,
                                float scale, void* stream);

@@ -168,7 +168,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared, "header parse failed"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load()                       # resolves every symbol, raises if one is missing
-    assert lib.mdgan_abi_version() == 1     # a host-only call
+    assert lib.mdgan_abi_version() == 2     # a host-only call
     assert lib.mdgan_wgrad_splits(128, 8, 8, 128, 64, 0) >= 1 and lib.mdgan_bn_workspace_floats(2, 4096, 128) > 0
 
 

@@ -81,15 +81,12 @@ def probe_wgrad(n, C1, C2, Hl, lbo=0, sbo=0):
     W = torch.zeros(C1, C2, 4, 4, dtype=torch.double, requires_grad=True)
     F.conv2d(xr, W, stride=2, padding=1).backward(dout.double())
     ref = W.grad
-    lib = _lib.load()
-    lib.mdgan_debug_set_wgrad_desc(lbo, sbo)
     splits = ops.wgrad_splits(n, Hl, Hl, C1, C2, 0)
     partial = torch.empty(splits * 16 * C1 * C2, device=dev)
     grad = torch.empty(C1, C2, 4, 4, device=dev)
     ops.wgrad_gemm(nhwc(dout).to(dev), nhwc(x).to(dev), partial, (n, Hl, Hl), 0, splits)
     ops.wgrad_unpack(partial, grad, 0, splits, C1, C1, C2)
     torch.cuda.synchronize()
-    lib.mdgan_debug_set_wgrad_desc(0, 0)
     return report(f"WGRAD n={n} C1={C1} C2={C2} Hl={Hl} splits={splits} lbo={lbo} sbo={sbo}", relerr(grad, ref))
 
 

@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Race hunt for the pipelined tensor-core kernels (TMA / mbarrier / TMEM hand-offs).
+
+Every kernel of the step has a fixed reduction order, so identical inputs must give identical BITS -- on every
+repetition, and across the kernel variants that implement the same arithmetic (shared-memory-operand kernel
+MDGAN_CONV_TA=0, tensor-memory-operand kernel with 1 / 2 / 3 transposer groups MDGAN_CONV_TG).  This tool runs the
+generator forward/backward and the discriminator training forward/backward of one plugin shape REPS times from
+identical state, reduces every intermediate buffer to a 64-bit checksum on the device (sum of the raw 32-bit
+patterns) and compares the checksum vector with the first repetition's, and optionally with a checksum file written
+by ANOTHER process (= another kernel variant).  A background stream writes random amounts of memory while the
+kernels run so that repetitions see different DRAM/L2 timing.  On the first mismatch it names the buffer and the
+repetition, dumps the offending tensor's diff statistics and keeps going (counts all mismatches).
+
+    python tools/stress_conv.py --dataset CIFAR10 --n 128 --reps 5000 --save /tmp/ref.pt      # e.g. MDGAN_CONV_TA=0
+    python tools/stress_conv.py --dataset CIFAR10 --n 128 --reps 5000 --against /tmp/ref.pt   # default kernels
+Also checks the first repetition's generated batch against the fp64 CPU module (the test's 1e-3 bar, reported).
+"""
+import argparse
+import copy
+import os
+import random
+import sys
+import time
+
+import torch
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "distributed-gan_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from util import init_model, plugin, relerr  # noqa: E402
+from mdgan_b200.nets import DiscNet, GenNet  # noqa: E402
+
+
+def buffers(net, extra):
+    out = []
+    for name in ("z", "a", "da", "dz"):
+        for i, t in enumerate(getattr(net, name)):
+            if t is not None:
+                out.append((f"{name}[{i}]", t))
+    out.append(("grad", net.state.grad))
+    out += list(extra.items())
+    return out
+
+
+def checksum(bufs):
+    return torch.stack([t.view(torch.int32).sum(dtype=torch.int64) for _, t in bufs])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dataset", default="CIFAR10")
+    ap.add_argument("--n", type=int, default=128)
+    ap.add_argument("--reps", type=int, default=2000)
+    ap.add_argument("--save", default=None)
+    ap.add_argument("--against", default=None)
+    ap.add_argument("--no-perturb", action="store_true")
+    ap.add_argument("--seconds", type=float, default=0.0, help="stop after this many seconds (0 = run all reps)")
+    a = ap.parse_args()
+
+    dev = torch.device("cuda:0")
+    mod = plugin(a.dataset)
+    n = a.n
+    g = torch.Generator().manual_seed(5)
+    z_host = torch.randn((n, mod.Z_DIM), generator=g)
+    z = z_host.to(dev)
+    s = (torch.randn((n, *mod.SHAPE), generator=g) * 0.01).to(dev)
+    real = (torch.rand((n // 2, *mod.SHAPE), generator=g) * 2 - 1).to(dev)
+    fake = torch.tanh(torch.randn((n // 2, *mod.SHAPE), generator=g)).to(dev)
+    Gm = init_model(mod.Generator, 9)
+    gen = GenNet(Gm, mod.Z_DIM, mod.SHAPE, n, dev, lr=2e-4, beta_1=0.5, beta_2=0.999)
+    disc = DiscNet(init_model(mod.Discriminator, 5), mod.SHAPE, n // 2, dev, lr=2e-4, beta_1=0.5, beta_2=0.999)
+    side = torch.cuda.Stream()
+    noise = torch.empty(64 * 1024 * 1024, device=dev)  # 256 MB
+    rnd = random.Random(7)
+
+    def one_rep():
+        if not a.no_perturb and rnd.random() < 0.7:
+            with torch.cuda.stream(side):
+                k = rnd.randrange(1, 64) * 1024 * 1024
+                noise[:k].fill_(rnd.random())
+        X = gen.forward(z)
+        gen.backward(s, 1.0 / 64)
+        disc.img[: n // 2].copy_(real)
+        disc.img[n // 2: n].copy_(fake)
+        disc.forward(disc.img, 2, disc.labels_train)
+        disc.backward(disc.img, 2, train=True)
+        return buffers(gen, {"X": X}) + [("D." + k, t) for k, t in buffers(disc, {"loss": disc.loss})]
+
+    bufs = one_rep()
+    names = [k for k, _ in bufs]
+    first = checksum(bufs)
+    torch.cuda.synchronize()
+    X64 = copy.deepcopy(Gm).double()(z_host.double().view(n, mod.Z_DIM, 1, 1))
+    x_err = relerr(gen.X, X64)
+    print(f"[stress_conv] {a.dataset} n={n}: first repetition X vs fp64 module {x_err:.2e}", flush=True)
+    ref = None
+    if a.against:
+        ref = torch.load(a.against)
+        assert ref["names"] == names and ref["dataset"] == a.dataset and ref["n"] == n
+        refsum = ref["checksums"].to(dev)
+        bad = (first != refsum).nonzero().flatten().tolist()
+        print(f"[stress_conv] vs {a.against} ({ref['variant']}): "
+              f"{'BIT-IDENTICAL' if not bad else 'DIFFERS in ' + ', '.join(names[i] for i in bad)}", flush=True)
+    mism = 0
+    t0 = time.time()
+    done = 1
+    for rep in range(1, a.reps):
+        bufs = one_rep()
+        chk = checksum(bufs)
+        if not torch.equal(chk, first):
+            bad = (chk != first).nonzero().flatten().tolist()
+            mism += 1
+            first_bad = names[bad[0]]
+            t = dict(bufs)[first_bad]
+            print(f"[stress_conv] rep {rep}: MISMATCH in {[names[i] for i in bad]}; first = {first_bad}, "
+                  f"absmax {t.abs().max().item():.3e}", flush=True)
+        done += 1
+        if a.seconds and time.time() - t0 > a.seconds:
+            break
+    torch.cuda.synchronize()
+    variant = f"TA={os.environ.get('MDGAN_CONV_TA', '1')} TG={os.environ.get('MDGAN_CONV_TG', 'default')} " \
+              f"WGRAD_TA={os.environ.get('MDGAN_WGRAD_TA', '1')}"
+    print(f"[stress_conv] {a.dataset} n={n} {variant}: {done} repetitions in {time.time() - t0:.1f} s, "
+          f"{'REPEATABLE' if mism == 0 else str(mism) + ' MISMATCHING REPETITIONS'}; X vs fp64 {x_err:.2e}", flush=True)
+    if a.save:
+        torch.save({"names": names, "checksums": first.cpu(), "dataset": a.dataset, "n": n, "variant": variant}, a.save)
+    ok = mism == 0 and x_err < 1e-3 and (ref is None or torch.equal(first, ref["checksums"].to(dev)))
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
