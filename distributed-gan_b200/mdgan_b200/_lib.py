@@ -20,7 +20,10 @@ _ll = C.c_longlong
 SIGNATURES = {
     "mdgan_abi_version": (_i, []),
     "mdgan_check_device": (_i, []),
-    "mdgan_conv_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _f, _p]),
+    "mdgan_conv_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _f, _p, _p]),
+    "mdgan_conv_rows_per_tile": (_i, [_i, _i, _i]),
+    "mdgan_bn_finalize": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _p]),
+    "mdgan_bn_apply": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "mdgan_wgrad_splits": (_i, [_i, _i, _i, _i, _i, _i]),
     "mdgan_wgrad_gemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_pack_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

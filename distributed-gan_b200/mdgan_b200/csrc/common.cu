@@ -89,6 +89,20 @@ int get_tmap_im2col_f32(const void* ptr, int n_img, int Hs, int Ws, int C, int b
   return 0;
 }
 
+cudaError_t configure_smem_once_impl(const void* kernel, int bytes) {
+  static std::map<std::pair<const void*, int>, int> done;
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find({kernel, dev});
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[{kernel, dev}] = bytes;
+  return e;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("MDGAN_PDL");  // opt-in: measured on B200 (round 1) it does not shorten the captured step

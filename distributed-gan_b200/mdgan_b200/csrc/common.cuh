@@ -68,18 +68,13 @@ int get_tmap_im2col_f32(const void* ptr, int n_img, int Hs, int Ws, int C, int b
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device): the attribute is per device,
-// so a process that drives several GPUs must set it on each of them.
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, so a process
+// that drives several GPUs must set it on each of them.  Keyed by the kernel's ADDRESS (instantiations of one template
+// share a function type).
+cudaError_t configure_smem_once_impl(const void* kernel, int bytes);
 template <typename K>
 inline cudaError_t configure_smem_once(K kernel, int bytes) {
-  static unsigned long long done = 0;  // bit d: configured on device d (d < 64)
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev < 64 && (done >> dev) & 1ULL) return cudaSuccess;
-  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess && dev < 64) done |= 1ULL << dev;
-  return e;
+  return configure_smem_once_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
 }  // namespace mdgan

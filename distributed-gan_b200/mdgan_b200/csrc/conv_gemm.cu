@@ -53,6 +53,8 @@ struct ConvGemmParams {
   const float* gate;  // optional, NHWC like dst: dst = result * act'(gate) (backward of the activation that produced
   int gate_act;       //   `gate`, fused into the data-gradient GEMM that feeds it; 1 ReLU, 2 LeakyReLU(gate_slope))
   float gate_slope;
+  float* bn_partial;  // optional [phases][row tiles][2][N_pad]: per-CTA column sums / sums of squares of the stored
+                      //   values (the BatchNorm statistics of the layer, finalized by mdgan_bn_finalize)
 };
 
 constexpr int kBM = 128;
@@ -98,9 +100,30 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
 // Epilogue of one 128 x BN tile: warp (q = TMEM lane quarter, half = column half) reads its 32 rows x BN/2 columns of
 // the kAccs accumulators (summed with round-to-nearest fp32 adds), applies bias / tanh / TF32 rounding / the fused
 // activation-backward gate and stores NHWC (float4) or scatters NCHW (optionally accumulating).
-template <int BN, int kAccs>
+// Sum of v[0..16) over the 32 lanes of the warp, column by column, with 16 shuffles instead of 80: at every step a lane
+// keeps half of its columns and hands the other half to its partner (xor 16, 8, 4, 2), then the pair is combined
+// (xor 1).  On return lane l holds, in v[0], the 32-row total of column (l >> 1) & 15.  Fixed tree: deterministic.
+__device__ __forceinline__ void warp_column_sums16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int mask = 16 >> step, cnt = 8 >> step;
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < cnt) {
+        const float send = upper ? v[j] : v[j + cnt];
+        const float keep = upper ? v[j + cnt] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+      }
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// red: shared-memory scratch [4 row quarters][2 statistics][BN] for the fused BatchNorm statistics (STATS only).
+template <int BN, int kAccs, bool STATS>
 __device__ __forceinline__ void conv_epilogue(const ConvGemmParams& p, uint32_t tmem_base, int q, int half, int lane,
-                                              int m0, int n0, int ph, int pw) {
+                                              int m0, int n0, int ph, int pw, float* red = nullptr) {
   constexpr int kColsPerHalf = (BN >= 32) ? BN / 2 : BN;
   if (BN >= 32 || half == 0) {
     const int row = q * 32 + lane;
@@ -127,7 +150,6 @@ __device__ __forceinline__ void conv_epilogue(const ConvGemmParams& p, uint32_t 
           for (int j = 0; j < 16; ++j) v[j] += t[j];
         }
       }
-        if (!ok) continue;
         const int nbase = n0 + col;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -137,6 +159,18 @@ __device__ __forceinline__ void conv_epilogue(const ConvGemmParams& p, uint32_t 
           if (p.round_tf32) x = round_to_tf32(x);
           v[j] = x;
         }
+        if (STATS && p.bn_partial != nullptr) {  // warp-uniform: every lane takes part in the shuffles
+          float s1[16], s2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { s1[j] = ok ? v[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+          warp_column_sums16(s1, lane);
+          warp_column_sums16(s2, lane);
+          if ((lane & 1) == 0) {
+            red[(q * 2 + 0) * BN + col + (lane >> 1)] = s1[0];
+            red[(q * 2 + 1) * BN + col + (lane >> 1)] = s2[0];
+          }
+        }
+        if (!ok) continue;
         if (!p.out_nchw) {
           const size_t oidx = (static_cast<size_t>((img * Ho + oh) * Wo + ow)) * p.N + nbase;
           float* o = p.dst + oidx;
@@ -298,7 +332,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
     // ------------------------------------------------------------------ epilogue
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after_sync();
-    conv_epilogue<BN, X3 ? S::kAccs : 1>(p, tmem_base, warp & 3, warp >> 2, lane, m0, n0, ph, pw);
+    conv_epilogue<BN, X3 ? S::kAccs : 1, false>(p, tmem_base, warp & 3, warp >> 2, lane, m0, n0, ph, pw);
     tc_fence_before_sync();
   } else if (warp == 8) {
     // ------------------------------------------------------------------ B producer (TMA)
@@ -388,7 +422,8 @@ struct ConvTaSmem {
   static constexpr int kBOff = kRawStages * kRawBytes;
   static constexpr int kBarOffset = kBOff + kBStages * kBStageBytes;
   static constexpr int kNumBars = 2 * kRawStages + 2 * kBStages + 2 * kAStages + 1;
-  static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kRedOff = kBarOffset + kNumBars * 8 + 16;   // [4][2][BN] floats: fused BatchNorm statistics
+  static constexpr int kTotal = kRedOff + 4 * 2 * BN * 4;
   static constexpr int kDynamic = kTotal + 1024;
   static constexpr int kMain = BN > 64 ? 2 : 4;
   static constexpr int kAccs = kMain + 1;
@@ -422,6 +457,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   uint64_t* a_empty = a_full + S::kAStages;
   uint64_t* tmem_full_bar = a_empty + S::kAStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* red = reinterpret_cast<float*>(smem + S::kRedOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -551,7 +587,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
       __syncwarp();
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after_sync();
-      conv_epilogue<BN, S::kAccs>(p, tmem_base, warp & 3, (warp - 4) >> 2, lane, m0, n0, ph, pw);
+      conv_epilogue<BN, S::kAccs, true>(p, tmem_base, warp & 3, (warp - 4) >> 2, lane, m0, n0, ph, pw, red);
       tc_fence_before_sync();
     }
   } else if (TMA_A && warp == 14) {
@@ -627,6 +663,13 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     __syncwarp();
     tc_fence_after_sync();
     tmem_dealloc<S::kTmemCols>(tmem_base);
+  }
+  if (p.bn_partial != nullptr && threadIdx.x < 2 * BN) {
+    // fused BatchNorm statistics: the CTA's column sums (quarters added in a fixed order) -> its partial slice
+    const int stat = threadIdx.x / BN, col = threadIdx.x - stat * BN;
+    const float t = (red[(0 * 2 + stat) * BN + col] + red[(1 * 2 + stat) * BN + col]) +
+                    (red[(2 * 2 + stat) * BN + col] + red[(3 * 2 + stat) * BN + col]);
+    p.bn_partial[((static_cast<size_t>(phase) * gridDim.x + blockIdx.x) * 2 + stat) * p.N_pad + n0 + col] = t;
   }
 }
 
@@ -711,11 +754,33 @@ static double conv_cost(int row_tiles, int phases, int n_pad, int bn, int ksteps
 using namespace mdgan;
 
 // See include/mdgan_b200.h for the contract.
+// Row tiling of the GEMM view: rows a CTA owns and, for the TMA-fed kernel, the box (images x grid rows x grid columns).
+static int conv_row_tiling(int Hg, int Wg, int precision, int* bn_img, int* bh, int* bw) {
+  *bn_img = *bh = *bw = 0;
+  if (precision == 1 && conv_ta_enabled() && conv_tma_enabled()) {
+    const int rows_img = Hg * Wg;
+    if (rows_img <= kBM && (kBM % rows_img == 0 || conv_tma_partial_enabled())) { *bn_img = kBM / rows_img; *bh = Hg; *bw = Wg; }
+    else if (Wg <= kBM && kBM % Wg == 0 && Hg % (kBM / Wg) == 0) { *bn_img = 1; *bh = kBM / Wg; *bw = Wg; }
+    if (*bn_img > 0) return *bn_img * *bh * *bw;
+  }
+  return kBM;
+}
+
+// GEMM rows one CTA of mdgan_conv_gemm owns for this row grid (callers size the fused-statistics buffer with it:
+// row tiles = ceil(n_img*Hg*Wg / rows)), or 0 when the fused BatchNorm statistics are not available in this mode.
+extern "C" int mdgan_conv_rows_per_tile(int Hg, int Wg, int precision) {
+  if (precision != 1 || !conv_ta_enabled() || Hg <= 0 || Wg <= 0) return 0;
+  int a, b, c;
+  return conv_row_tiling(Hg, Wg, precision, &a, &b, &c);
+}
+
 extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img,
                                int Hg, int Wg, int Hs, int Ws, int C, int mode, int N, int N_pad, int out_nchw,
                                int act, int round_tf32, int accumulate, int precision, int force_bn, const float* gate,
-                               int gate_act, float gate_slope, void* stream) {
+                               int gate_act, float gate_slope, float* bn_partial, void* stream) {
   if (!src || !wpacked || !dst) return MDGAN_ERR_BAD_ARG;
+  if (bn_partial && (precision != 1 || !conv_ta_enabled() || out_nchw || gate || act != 0 || accumulate))
+    return MDGAN_ERR_UNSUPPORTED;
   if (gate && (out_nchw || (gate_act != 1 && gate_act != 2))) return MDGAN_ERR_UNSUPPORTED;
   if (C <= 0 || C % kBK != 0 || mode < 0 || mode > 2) return MDGAN_ERR_UNSUPPORTED;
   if (N_pad % 16 != 0 || N > N_pad || N <= 0) return MDGAN_ERR_UNSUPPORTED;
@@ -727,6 +792,7 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   p.round_tf32 = round_tf32;
   p.accumulate = accumulate;
   p.gate = gate; p.gate_act = gate_act; p.gate_slope = gate_slope;
+  p.bn_partial = bn_partial;
   if (accumulate && !out_nchw) return MDGAN_ERR_UNSUPPORTED;
   if (p.M <= 0) return MDGAN_ERR_BAD_ARG;
   const int taps = mode == 0 ? 16 : (mode == 1 ? 4 : 1);
@@ -735,13 +801,7 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   // TMA-fed activation tile (tf32x3 TMEM-operand kernel): the rows of a CTA must be a box of the (n, i, j) grid --
   // whole images (as many as fit in 128 rows; 7x7 grids give 98-row tiles) or whole grid rows of one image.
   int bn_img = 0, bh = 0, bw = 0;
-  p.rows_per_tile = kBM;
-  if (precision == 1 && conv_ta_enabled() && conv_tma_enabled()) {
-    const int rows_img = Hg * Wg;
-    if (rows_img <= kBM && (kBM % rows_img == 0 || conv_tma_partial_enabled())) { bn_img = kBM / rows_img; bh = Hg; bw = Wg; }
-    else if (Wg <= kBM && kBM % Wg == 0 && Hg % (kBM / Wg) == 0) { bn_img = 1; bh = kBM / Wg; bw = Wg; }
-    if (bn_img > 0) p.rows_per_tile = bn_img * bh * bw;
-  }
+  p.rows_per_tile = conv_row_tiling(Hg, Wg, precision, &bn_img, &bh, &bw);
   const int row_tiles = ceil_div(p.M, p.rows_per_tile);
   const bool x3 = precision == 1;
   // Tile width: the candidate (dividing N_pad) with the lowest estimated time -- wide tiles use the tensor core

@@ -283,6 +283,59 @@ bn_stats_kernel(const float* __restrict__ x, float* __restrict__ partial, unsign
   }
 }
 
+// Finalize kernel for statistics reduced by the producing GEMM (mdgan_conv_gemm, bn_partial): block = 8 channels x 32
+// lanes; a channel's lanes walk its partial slices (phase, tile, fold) in a fixed strided order, accumulate in fp64 and
+// are combined by a butterfly; then exactly the arithmetic of bn_stats_kernel's last block.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ partial, int phases, int row_tiles, int tiles_per_group, int col_stride,
+                   int fold, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
+                   float* __restrict__ stats, int G, int Pg, int C, float eps, float momentum) {
+  pdl_enter();
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;  // whole warps: C % 8 == 0 is required by the launcher
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += G;
+  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+  const float gm = gamma[c], bt = beta[c];
+  const int per_group = phases * tiles_per_group * fold;
+  for (int g = 0; g < G; ++g) {
+    double sum = 0.0, sq = 0.0;
+    for (int i = lane; i < per_group; i += 32) {
+      const int f = i % fold, r = i / fold;
+      const int t = r % tiles_per_group, ph = r / tiles_per_group;
+      const float* sl = partial + (static_cast<long long>(ph) * row_tiles + g * tiles_per_group + t) * 2 * col_stride +
+                        f * C + c;
+      sum += __ldcg(sl);
+      sq += __ldcg(sl + col_stride);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const double mean = sum / Pg;
+    double var = sq / Pg - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gm * invstd;
+    const float unbiased = (float)(var * ((double)Pg / (double)(Pg > 1 ? Pg - 1 : 1)));
+    rm = (1.f - momentum) * rm + momentum * (float)mean;
+    rv = (1.f - momentum) * rv + momentum * unbiased;
+    if (lane == 0) {
+      float* st = stats + (long long)g * 4 * C;
+      st[c] = (float)mean;
+      st[C + c] = invstd;
+      st[2 * C + c] = sc;
+      st[3 * C + c] = bt - (float)mean * sc;
+    }
+  }
+  if (lane == 0) {
+    if (running_mean) running_mean[c] = rm;
+    if (running_var) running_var[c] = rv;
+  }
+}
+
 // act: 0 none, 1 ReLU, 2 LeakyReLU(slope)
 __device__ __forceinline__ float act_fwd(float y, int act, float slope) {
   if (act == 1) return y > 0.f ? y : 0.f;
@@ -682,6 +735,30 @@ extern "C" int mdgan_bn_forward(const float* x, float* out, const float* gamma, 
   const long long total4 = (long long)G * Pg * C / 4;
   MDGAN_LAUNCH(bn_apply_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, x, stats, out, Pg, C, total4, act, slope,
                round_tf32);
+  return 0;
+}
+
+extern "C" int mdgan_bn_finalize(const float* partial, int phases, int row_tiles, int tiles_per_group, int col_stride,
+                                 int fold, const float* gamma, const float* beta, float* running_mean,
+                                 float* running_var, long long* num_batches_tracked, float* stats, int G, int Pg, int C,
+                                 float eps, float momentum, void* stream) {
+  if (!partial || !gamma || !beta || !stats) return MDGAN_ERR_BAD_ARG;
+  if (C % 8 != 0 || G < 1 || Pg < 1 || phases < 1 || fold < 1 || tiles_per_group < 1 || G * tiles_per_group > row_tiles ||
+      fold * C > col_stride)
+    return MDGAN_ERR_UNSUPPORTED;
+  MDGAN_LAUNCH(bn_finalize_kernel, dim3(C / 8), dim3(256), 0, (cudaStream_t)stream, partial, phases, row_tiles,
+               tiles_per_group, col_stride, fold, gamma, beta, running_mean, running_var, num_batches_tracked, stats, G, Pg,
+               C, eps, momentum);
+  return 0;
+}
+
+extern "C" int mdgan_bn_apply(const float* x, const float* stats, float* out, int G, int Pg, int C, int act, float slope,
+                              int round_tf32, void* stream) {
+  if (!x || !stats || !out) return MDGAN_ERR_BAD_ARG;
+  if (C % 4 != 0 || G < 1 || Pg < 1) return MDGAN_ERR_UNSUPPORTED;
+  const long long total4 = (long long)G * Pg * C / 4;
+  MDGAN_LAUNCH(bn_apply_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, (cudaStream_t)stream, x, stats, out, Pg, C,
+               total4, act, slope, round_tf32);
   return 0;
 }
 

@@ -274,9 +274,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
 // registers and writes its TMEM lane (tcgen05.st).  The MMAs read A from TMEM; only the Hi operand (N side) is still
 // produced through shared memory by the eight producer warps.  Shared-memory/L1 traffic per K step: 32 KB for Lo
 // (TMA write + one read) instead of 112 KB (L1 fill + read, hi/lo stores, three MMA reads).
-//   warps 0-3 : transposers            warps 4-11: Hi producers, then the epilogue
-//   warp 12   : Lo TMA issuer (lane 0) + TMEM allocator + single-thread MMA issuer (lane 0 of warp 13)
-constexpr int kWTaThreads = (4 + kWProducerWarps + 2) * 32;
+//   warps 0..4*TG-1 : TG groups of four transposer warps (group g takes K steps g, g+TG, ...; one group's chain of
+//                     wait raw -> 32 LDS -> split -> wait TMEM stage -> 2 tcgen05.st -> wait::st -> arrive is longer
+//                     than the MMA time of a K step, so consecutive K steps are transposed concurrently)
+//   next 8 warps    : Hi producers, then the epilogue
+//   next warp       : Lo TMA issuer (lane 0);  last warp: TMEM allocator + single-thread MMA issuer (lane 0)
+template <int TG>
+constexpr int wta_threads() { return (4 * TG + kWProducerWarps + 2) * 32; }
 
 template <int BN>
 struct WgradTaSmem {
@@ -284,7 +288,7 @@ struct WgradTaSmem {
   static constexpr int kStageBytes = 2 * kBBytes;         // [B_hi | B_lo]
   static constexpr int kStages = 3;
   static constexpr int kRawBytes = (kWM / 32) * kWK * 128;  // 16 KB raw Lo tile
-  static constexpr int kRawStages = 3;
+  static constexpr int kRawStages = 4;
   static constexpr int kAStages = BN > 64 ? 2 : 3;        // TMEM stages of [A_hi (32 columns) | A_lo (32 columns)]
   static constexpr int kRawOff = kStages * kStageBytes;
   static constexpr int kBarOffset = kRawOff + kRawStages * kRawBytes;
@@ -297,10 +301,13 @@ struct WgradTaSmem {
   static_assert(kACol0 + kAStages * 64 <= 512, "TMEM holds 512 columns");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kWTaThreads, 1)
+template <int BN, int TG>
+__global__ void __launch_bounds__(wta_threads<TG>(), 1)
 wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradParams p) {
   using S = WgradTaSmem<BN>;
+  constexpr int kProd0 = 4 * TG;                       // first Hi-producer warp
+  constexpr int kTmaWarp = kProd0 + kWProducerWarps;   // Lo TMA issuer
+  constexpr int kMmaWarp = kTmaWarp + 1;               // TMEM allocator + MMA issuer
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
@@ -333,22 +340,23 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
     mbar_init(tmem_full_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 12 && lane == 0) tma_prefetch_desc(&tmap_lo);
-  if (warp == 13) tmem_alloc<S::kTmemCols>(tmem_ptr_smem);
+  if (warp == kTmaWarp && lane == 0) tma_prefetch_desc(&tmap_lo);
+  if (warp == kMmaWarp) tmem_alloc<S::kTmemCols>(tmem_ptr_smem);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
 
-  if (warp < 4) {
+  if (warp < kProd0) {
     // ---------------------------------------------------------------- transposers: raw Lo tile -> TMEM lane (= channel)
-    const uint32_t grp = smem_u32(smem) + S::kRawOff + warp * (kWK * 128);  // this warp's 32-channel group
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + S::kACol0;
+    const int wq = warp & 3;
+    const uint32_t grp = smem_u32(smem) + S::kRawOff + wq * (kWK * 128);  // this warp's 32-channel group
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + S::kACol0;
     const uint32_t cword = (lane & 3) * 4, cchunk = lane >> 2;
-    int s = 0, t = 0;
-    uint32_t pars = 0, part = 0;
-    for (int it = 0; it < ksteps; ++it) {
+    for (int it = warp >> 2; it < ksteps; it += TG) {
+      const int s = it % S::kRawStages, t = it % S::kAStages;
+      const uint32_t pars = (it / S::kRawStages) & 1, part = (it / S::kAStages) & 1;
       mbar_wait(&raw_full[s], pars);
       float x[32];
 #pragma unroll
@@ -372,12 +380,10 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[t]);
-      if (++s == S::kRawStages) { s = 0; pars ^= 1; }
-      if (++t == S::kAStages) { t = 0; part ^= 1; }
     }
-  } else if (warp < 4 + kWProducerWarps) {
+  } else if (warp < kTmaWarp) {
     // ---------------------------------------------------------------- Hi producers (shared memory), then epilogue
-    const int tid = threadIdx.x - 128;
+    const int tid = threadIdx.x - kProd0 * 32;
     const uint32_t smem0 = smem_u32(smem);
     constexpr int kBChunksPerRow = BN / 4;
     constexpr int kBRowsPerPass = 256 / kBChunksPerRow;
@@ -440,7 +446,7 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after_sync();
     }
-    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int q = warp & 3, half = (warp - kProd0) >> 2;
     constexpr int kColsPerHalf = BN / 2;
     const int c1 = c1_0 + q * 32 + lane;
     const int taps = gridDim.z / p.splits;
@@ -469,7 +475,7 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
       }
     }
     tc_fence_before_sync();
-  } else if (warp == 12) {
+  } else if (warp == kTmaWarp) {
     // ---------------------------------------------------------------- Lo TMA issuer: 4 boxes of 32 pixels x 32 channels
     if (lane == 0) {
       int s = 0;
@@ -518,20 +524,35 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
     }
   }
   __syncthreads();
-  if (warp == 13) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     tc_fence_after_sync();
     tmem_dealloc<S::kTmemCols>(tmem_base);
   }
 }
 
-template <int BN>
-static int launch_wgrad_ta(const CUtensorMap& tmap_lo, const WgradParams& p, dim3 grid, cudaStream_t st) {
+template <int BN, int TG>
+static int launch_wgrad_ta_tg(const CUtensorMap& tmap_lo, const WgradParams& p, dim3 grid, cudaStream_t st) {
   using S = WgradTaSmem<BN>;
   static_assert(S::kDynamic <= 227 * 1024, "shared memory per CTA");
-  MDGAN_CUDA(configure_smem_once(wgrad_gemm_ta_kernel<BN>, S::kDynamic));
-  MDGAN_LAUNCH((wgrad_gemm_ta_kernel<BN>), grid, dim3(kWTaThreads), S::kDynamic, st, tmap_lo, p);
+  MDGAN_CUDA(configure_smem_once(wgrad_gemm_ta_kernel<BN, TG>, S::kDynamic));
+  MDGAN_LAUNCH((wgrad_gemm_ta_kernel<BN, TG>), grid, dim3(wta_threads<TG>()), S::kDynamic, st, tmap_lo, p);
   return 0;
+}
+
+// MDGAN_WGRAD_TG = 1 | 2 (default 2): groups of transposer warps (see wgrad_gemm_ta_kernel).
+static int wgrad_tg() {
+  static const int tg = [] {
+    const char* e = getenv("MDGAN_WGRAD_TG");
+    const int v = e ? atoi(e) : 2;
+    return v < 1 ? 1 : (v > 2 ? 2 : v);
+  }();
+  return tg;
+}
+
+template <int BN>
+static int launch_wgrad_ta(const CUtensorMap& tmap_lo, const WgradParams& p, dim3 grid, cudaStream_t st) {
+  return wgrad_tg() == 1 ? launch_wgrad_ta_tg<BN, 1>(tmap_lo, p, grid, st) : launch_wgrad_ta_tg<BN, 2>(tmap_lo, p, grid, st);
 }
 
 // MDGAN_WGRAD_TA = 1 (default) | 0: Lo operand by TMA into tensor memory (tf32x3 only; same arithmetic, same bits).

@@ -17,6 +17,7 @@ Data layout in HBM (per net):
 from __future__ import annotations
 
 import copy
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -26,6 +27,32 @@ from . import ops
 from .plan import ACT_LRELU, ACT_RELU, ConvLayer, NetPlan, extract_plan
 
 _ACT_CODE = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "lrelu": ops.ACT_LRELU}
+# MDGAN_BN_FUSED_STATS = 1 (default) | 0: BatchNorm statistics reduced in the producing GEMM's epilogue (no separate
+# pass over the layer output) wherever a CTA's rows belong to one BatchNorm pass; 0 keeps the two-kernel bn_forward.
+_FUSED_STATS = os.environ.get("MDGAN_BN_FUSED_STATS", "1") == "1"
+
+
+def _stats_floats(plan, n_pad: int) -> int:
+    row_tiles, _, phases = plan
+    return phases * row_tiles * 2 * n_pad
+
+
+def _conv_bn_act(src, wpacked, mode, c_out, z, a, grid, src_hw, bias, prec, bn_part, bnp, P, B, stats, bn_ws, bn_cnt, G, Pg,
+                 act, slope, round_tf32, n_cols=None, fold=1):
+    """conv_gemm -> train-mode BatchNorm -> activation.  With fused statistics: GEMM (+ column sums in its epilogue) ->
+    bn_finalize -> bn_apply; otherwise GEMM -> bn_forward (statistics pass + apply)."""
+    n_cols = c_out if n_cols is None else n_cols
+    plan = ops.conv_stats_plan(grid, mode, G, prec) if (_FUSED_STATS and bn_part is not None) else None
+    nbt = B[bnp.num_batches_tracked] if bnp.num_batches_tracked else None
+    if plan is not None and _stats_floats(plan, ops.n_pad_for(n_cols)) <= bn_part.numel():
+        ops.conv_gemm(src, wpacked, mode, n_cols, z, grid, src_hw, bias=bias, precision=prec, bn_partial=bn_part)
+        ops.bn_finalize(bn_part, plan, ops.n_pad_for(n_cols), fold, P[bnp.weight], P[bnp.bias], B[bnp.running_mean],
+                        B[bnp.running_var], nbt, stats, G, Pg, c_out, eps=bnp.eps, momentum=bnp.momentum)
+        ops.bn_apply(z, stats, a, G, Pg, c_out, act, slope, round_tf32=round_tf32)
+        return
+    ops.conv_gemm(src, wpacked, mode, n_cols, z, grid, src_hw, bias=bias, precision=prec)
+    ops.bn_forward(z, a, P[bnp.weight], P[bnp.bias], B[bnp.running_mean], B[bnp.running_var], nbt, stats, bn_ws, bn_cnt, G,
+                   Pg, c_out, act, slope, round_tf32=round_tf32, eps=bnp.eps, momentum=bnp.momentum)
 
 
 def _pad(n: int, m: int) -> int:
@@ -183,6 +210,14 @@ class DiscNet:
                 self.partial.append(torch.empty(ops.thin_wgrad_slices(nmax, Ho, Ho) * Cc * ly.c_in * 16, **f))
         self.bn_ws = torch.empty(max(ws, 1), **f)
         self.bn_cnt = ops.bn_counters(device)
+        part = 0
+        for l, ly in enumerate(L[:-1]):
+            if ly.bn and l >= 1:
+                for G in range(1, max_groups + 1):
+                    plan = ops.conv_stats_plan((G * batch_size, ly.h_out, ly.h_out), ops.MODE_DOWN, G, self.prec)
+                    if plan is not None:
+                        part = max(part, _stats_floats(plan, ops.n_pad_for(ly.c_out)))
+        self.bn_part = torch.empty(part, **f) if part else None
         head = L[-1]
         self.w_head = torch.empty(head.k * head.k * head.c_in, **f)
         self.prob = torch.zeros(nmax, **f)
@@ -227,13 +262,10 @@ class DiscNet:
         for l in range(1, len(L) - 1):
             ly = L[l]
             Ho = ly.h_out
-            ops.conv_gemm(self.a[l - 1][:n], self.wp[l], ops.MODE_DOWN, ly.c_out, self.z[l][:n], (n, Ho, Ho),
-                          (ly.h_in, ly.h_in), bias=P[ly.bias] if ly.bias else None, precision=self.prec)
-            bn = ly.bn
-            ops.bn_forward(self.z[l][:n], self.a[l][:n], P[bn.weight], P[bn.bias], B[bn.running_mean], B[bn.running_var],
-                           B[bn.num_batches_tracked] if bn.num_batches_tracked else None, self.stats[l], self.bn_ws,
-                           self.bn_cnt, G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope,
-                           round_tf32=(self.rnd and L[l + 1].kind == "down"), eps=bn.eps, momentum=bn.momentum)
+            _conv_bn_act(self.a[l - 1][:n], self.wp[l], ops.MODE_DOWN, ly.c_out, self.z[l][:n], self.a[l][:n], (n, Ho, Ho),
+                         (ly.h_in, ly.h_in), P[ly.bias] if ly.bias else None, self.prec, self.bn_part, ly.bn, P, B,
+                         self.stats[l], self.bn_ws, self.bn_cnt, G, b * Ho * Ho, _ACT_CODE[ly.act], ly.slope,
+                         self.rnd and L[l + 1].kind == "down")
         head = L[-1]
         ops.head_forward(self.a[-1][:n], self.w_head, labels, self.prob, self.loss_terms, self.dlogit, self.loss,
                          self.head_counter, G, b, head.k * head.k, head.c_in)
@@ -328,6 +360,15 @@ class GenNet:
         self.bn_cnt = ops.bn_counters(device)
         l0 = L[0]
         self.kk = l0.k * l0.k
+        part = 0
+        plan = ops.conv_stats_plan((n, 1, 1), ops.MODE_DENSE, 1, self.prec)
+        if plan is not None:
+            part = _stats_floats(plan, ops.n_pad_for(self.kk * l0.c_out))
+        for ly in L[1:-1]:
+            plan = ops.conv_stats_plan((n, ly.h_in, ly.h_in), ops.MODE_UP, 1, self.prec)
+            if plan is not None:
+                part = max(part, _stats_floats(plan, ops.n_pad_for(ly.c_out)))
+        self.bn_part = torch.empty(part, **f) if part else None
         self.wp_dense = torch.empty(ops.packed_shape(ops.MODE_DENSE, l0.c_out, z_dim, self.kk, self.prec), **f)
         sp0 = ops.wgrad_splits(n, 1, 1, self.zc, self.kk * l0.c_out, ops.MODE_DENSE)
         self.partial.append(torch.empty(sp0 * self.zc * self.kk * l0.c_out, **f))
@@ -369,19 +410,17 @@ class GenNet:
         """z [n, z_dim] (device) -> X NCHW [n, C, H, W]; train-mode BatchNorm over all n samples (server.py:219-220)."""
         n, P, B, L = self.n, self.state.p, self.state.b, self.L
         ops.pad_rows(z.view(n, self.z_dim), self.zp, round_tf32=self.rnd)
-        l0 = L[0]
-        ops.conv_gemm(self.zp, self.wp_dense, ops.MODE_DENSE, self.kk * l0.c_out, self.z[0], (n, 1, 1), (1, 1),
-                      precision=self.prec)
         for l in range(len(L) - 1):
-            ly, bn = L[l], L[l].bn
+            ly = L[l]
             Ho = ly.h_out
-            if l >= 1:
-                ops.conv_gemm(self.a[l - 1], self.wq[l], ops.MODE_UP, ly.c_out, self.z[l], (n, ly.h_in, ly.h_in),
-                              (ly.h_in, ly.h_in), precision=self.prec)
-            ops.bn_forward(self.z[l], self.a[l], P[bn.weight], P[bn.bias], B[bn.running_mean], B[bn.running_var],
-                           B[bn.num_batches_tracked] if bn.num_batches_tracked else None, self.stats[l], self.bn_ws,
-                           self.bn_cnt, 1, n * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd, eps=bn.eps,
-                           momentum=bn.momentum)
+            if l == 0:   # ConvTranspose2d on a 1x1 input: GEMM columns are (position, channel)
+                _conv_bn_act(self.zp, self.wp_dense, ops.MODE_DENSE, ly.c_out, self.z[0], self.a[0], (n, 1, 1), (1, 1), None,
+                             self.prec, self.bn_part, ly.bn, P, B, self.stats[0], self.bn_ws, self.bn_cnt, 1, n * Ho * Ho,
+                             _ACT_CODE[ly.act], ly.slope, self.rnd, n_cols=self.kk * ly.c_out, fold=self.kk)
+            else:
+                _conv_bn_act(self.a[l - 1], self.wq[l], ops.MODE_UP, ly.c_out, self.z[l], self.a[l], (n, ly.h_in, ly.h_in),
+                             (ly.h_in, ly.h_in), None, self.prec, self.bn_part, ly.bn, P, B, self.stats[l], self.bn_ws,
+                             self.bn_cnt, 1, n * Ho * Ho, _ACT_CODE[ly.act], ly.slope, self.rnd)
         last = L[-1]
         ops.thin_up(self.a[-1], P[last.weight], self.X, act_tanh=True)
         return self.X

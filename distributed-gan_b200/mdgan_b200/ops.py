@@ -1,8 +1,9 @@
-"""Tensor-level wrappers over the C-ABI launchers (one function per exported kernel family).
+"""Tensor-level wrappers over the kernel library (one function per exported kernel family).
 
-Activations are NHWC fp32 CUDA tensors, parameters keep their PyTorch layout.  Every wrapper launches on
-torch's current CUDA stream, so the calls can be captured into a CUDA graph.  No fallback: a non-CUDA tensor
-or a failed launch raises.
+Every launch goes through the torch custom-op layer `torch.ops.mdgan_b200.*` (mdgan_b200/torch_ops.py), a thin shim
+over the C-ABI of include/mdgan_b200.h: tensors in, raw device pointers + sizes + the current CUDA stream out.
+Activations are NHWC fp32 CUDA tensors, parameters keep their PyTorch layout.  Launches are stream-ordered, so the
+calls can be captured into a CUDA graph.  No fallback: a non-CUDA tensor or a failed launch raises.
 """
 from __future__ import annotations
 
@@ -12,6 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
+from .torch_ops import ns as _K
 
 import os
 
@@ -41,10 +43,10 @@ def set_observer(observer) -> None:
 
 def _run(name: str, n_kernels: int, flops: float, nbytes: float, call) -> None:
     if _observer is None:
-        _lib.check(call(), name)
+        call()
         return
     with _observer(name, n_kernels, flops, nbytes):
-        _lib.check(call(), name)
+        call()
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -139,7 +141,7 @@ def pack_down(W: torch.Tensor, out: Optional[torch.Tensor] = None, precision: in
     if out is None:
         out = torch.empty(packed_shape(MODE_DOWN, N, Cc, precision=precision), device=W.device, dtype=torch.float32)
     _run("pack_weights", 1, 0, 4 * (W.numel() + out.numel()),
-         lambda: _lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 0, N, Cc, Np, Cp, 16, _split_of(out, Np), _stream()))
+         lambda: _K.pack_weights(W, out, 0, N, Cc, Np, Cp, 16, _split_of(out, Np)))
     return out
 
 
@@ -150,8 +152,7 @@ def pack_up(W: torch.Tensor, out: Optional[torch.Tensor] = None, precision: int 
     if out is None:
         out = torch.empty(packed_shape(MODE_UP, N, Cc, precision=precision), device=W.device, dtype=torch.float32)
     _run("pack_weights", 1, 0, 4 * (W.numel() + out.numel()),
-         lambda: _lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 1, N, Cc, Np, Cp, 16, _split_of(out, 4 * Np),
-                                                _stream()))
+         lambda: _K.pack_weights(W, out, 1, N, Cc, Np, Cp, 16, _split_of(out, 4 * Np)))
     return out
 
 
@@ -162,8 +163,7 @@ def pack_dense(W: torch.Tensor, out: Optional[torch.Tensor] = None, precision: i
     if out is None:
         out = torch.empty(packed_shape(MODE_DENSE, N, Cc, KK, precision), device=W.device, dtype=torch.float32)
     _run("pack_weights", 1, 0, 4 * (W.numel() + out.numel()),
-         lambda: _lib.load().mdgan_pack_weights(_ptr(W), _ptr(out), 2, N, Cc, KK * N, Cp, KK, _split_of(out, KK * N),
-                                                _stream()))
+         lambda: _K.pack_weights(W, out, 2, N, Cc, KK * N, Cp, KK, _split_of(out, KK * N)))
     return out
 
 
@@ -218,7 +218,7 @@ class PackPlan:
         if self.table is None:
             self.finalize()
         _run("pack_weights", 1, 0, self.nbytes,
-             lambda: _lib.load().mdgan_pack_weights_multi(_ptr(self.table), len(self.jobs), self.blocks, _stream()))
+             lambda: _K.pack_weights_multi(self.table, len(self.jobs), self.blocks))
 
 
 # ----------------------------------------------------------------------------- tensor-core GEMMs
@@ -226,10 +226,12 @@ def conv_gemm(src: torch.Tensor, wpacked: torch.Tensor, mode: int, N: int, out: 
               grid: Tuple[int, int, int], src_hw: Tuple[int, int], bias: Optional[torch.Tensor] = None,
               out_nchw: bool = False, act_tanh: bool = False, round_tf32: bool = False, accumulate: bool = False,
               precision: int = TF32, force_bn: int = 0, gate: Optional[torch.Tensor] = None, gate_act: int = ACT_NONE,
-              gate_slope: float = 0.0) -> torch.Tensor:
+              gate_slope: float = 0.0, bn_partial: Optional[torch.Tensor] = None) -> torch.Tensor:
     """grid = (n_img, Hg, Wg): the low-resolution row grid; src is NHWC [n_img, Hs, Ws, C].  With precision TF32X3
     `wpacked` must hold the hi and lo matrices (pack_*(..., precision=TF32X3)).  gate (NHWC, shaped like out): the
-    result is multiplied by act'(gate) -- the (Leaky)ReLU backward fused into the data gradient that feeds it."""
+    result is multiplied by act'(gate) -- the (Leaky)ReLU backward fused into the data gradient that feeds it.
+    bn_partial ([phases * row tiles, 2, N_pad], see conv_stats_shape): the GEMM epilogue also reduces the BatchNorm
+    statistics of its output; finish with bn_finalize + bn_apply instead of bn_forward."""
     n_img, Hg, Wg = grid
     Hs, Ws = src_hw
     Cc = src.shape[-1]
@@ -239,11 +241,28 @@ def conv_gemm(src: torch.Tensor, wpacked: torch.Tensor, mode: int, N: int, out: 
     flops = 2.0 * n_img * Hg * Wg * taps * Cc * N
     nbytes = 4.0 * (src.numel() + out.numel() + wpacked.numel())
     _run(("conv_down", "conv_up", "conv_dense")[mode], 1, flops, nbytes,
-         lambda: _lib.load().mdgan_conv_gemm(_ptr(src), _ptr(wpacked), _ptr(out), _ptr(bias), n_img, Hg, Wg, Hs, Ws, Cc,
+         lambda: _K.conv_gemm(src, wpacked, out, bias, n_img, Hg, Wg, Hs, Ws, Cc,
                                              mode, N, N_pad, int(out_nchw), int(act_tanh), int(round_tf32),
-                                             int(accumulate), precision, force_bn, _ptr(gate), gate_act,
-                                             float(gate_slope), _stream()))
+                                             int(accumulate), precision, force_bn, gate, gate_act,
+                                             float(gate_slope), bn_partial))
     return out
+
+
+def conv_rows_per_tile(Hg: int, Wg: int, precision: int) -> int:
+    """GEMM rows one CTA of conv_gemm owns (0: the fused BatchNorm statistics are unavailable in this mode)."""
+    return _lib.load().mdgan_conv_rows_per_tile(Hg, Wg, precision)
+
+
+def conv_stats_plan(grid: Tuple[int, int, int], mode: int, groups: int, precision: int):
+    """(row_tiles, tiles_per_group, phases) of the fused statistics of conv_gemm over `grid` = (n_img, Hg, Wg) holding
+    `groups` equally sized BatchNorm passes, or None when a CTA's rows would straddle two passes / the mode has no
+    fused statistics (callers then use bn_forward)."""
+    n_img, Hg, Wg = grid
+    rpt = conv_rows_per_tile(Hg, Wg, precision)
+    M = n_img * Hg * Wg
+    if rpt <= 0 or M % groups != 0 or (M // groups) % rpt != 0:
+        return None
+    return M // rpt, M // groups // rpt, 4 if mode == MODE_UP else 1
 
 
 def wgrad_splits(n_img: int, Hl: int, Wl: int, C1: int, C2: int, mode: int) -> int:
@@ -257,21 +276,21 @@ def wgrad_gemm(lo: torch.Tensor, hi: torch.Tensor, partial: torch.Tensor, grid: 
     flops = 2.0 * n_img * Hl * Wl * taps * lo.shape[-1] * hi.shape[-1]
     nbytes = 4.0 * (lo.numel() + hi.numel() + taps * lo.shape[-1] * hi.shape[-1])
     _run("wgrad_gemm", 1, flops, nbytes,
-         lambda: _lib.load().mdgan_wgrad_gemm(_ptr(lo), _ptr(hi), _ptr(partial), n_img, Hl, Wl, lo.shape[-1],
-                                              hi.shape[-1], mode, splits, precision, _stream()))
+         lambda: _K.wgrad_gemm(lo, hi, partial, n_img, Hl, Wl, lo.shape[-1],
+                                              hi.shape[-1], mode, splits, precision))
     return partial
 
 
 def wgrad_unpack(partial: torch.Tensor, grad: torch.Tensor, mode: int, splits: int, C1: int, C1p: int, C2: int,
                  N: int = 0, KK: int = 0) -> torch.Tensor:
     _run("wgrad_unpack", 1, 0, 4.0 * grad.numel() * (splits + 1),
-         lambda: _lib.load().mdgan_wgrad_unpack(_ptr(partial), _ptr(grad), mode, splits, C1, C1p, C2, N, KK, _stream()))
+         lambda: _K.wgrad_unpack(partial, grad, mode, splits, C1, C1p, C2, N, KK))
     return grad
 
 
 def reduce_slices(partial: torch.Tensor, out: torch.Tensor, slices: int) -> torch.Tensor:
     _run("reduce_slices", 1, 0, 4.0 * out.numel() * (slices + 1),
-         lambda: _lib.load().mdgan_reduce_slices(_ptr(partial), _ptr(out), slices, out.numel(), _stream()))
+         lambda: _K.reduce_slices(partial, out, slices, out.numel()))
     return out
 
 
@@ -280,8 +299,8 @@ def thin_down(img: torch.Tensor, W: torch.Tensor, out: torch.Tensor, act: int = 
               round_tf32: bool = False) -> torch.Tensor:
     n, ci, Hi, Wi = img.shape
     _run("thin_down", 1, 2.0 * out.numel() * 16 * ci, 4.0 * (img.numel() + out.numel() + W.numel()),
-         lambda: _lib.load().mdgan_thin_down(_ptr(img), _ptr(W), _ptr(out), n, ci, Hi, Wi, W.shape[0], act, slope,
-                                             int(round_tf32), _stream()))
+         lambda: _K.thin_down(img, W, out, n, ci, Hi, Wi, W.shape[0], act, slope,
+                                             int(round_tf32)))
     return out
 
 
@@ -291,8 +310,8 @@ def thin_up(src: torch.Tensor, W: torch.Tensor, out: torch.Tensor, act_tanh: boo
     n, H, Wd, Cc = src.shape
     N = W.shape[1]
     _run("thin_up", 1, 2.0 * n * H * Wd * 16 * Cc * N, 4.0 * (src.numel() + out.numel() * (2 if accumulate else 1)),
-         lambda: _lib.load().mdgan_thin_up(_ptr(src), _ptr(W), _ptr(out), n, H, Wd, Cc, N, int(act_tanh),
-                                           int(accumulate), _stream()))
+         lambda: _K.thin_up(src, W, out, n, H, Wd, Cc, N, int(act_tanh),
+                                           int(accumulate)))
     return out
 
 
@@ -304,7 +323,7 @@ def thin_wgrad(feat: torch.Tensor, img: torch.Tensor, partial: torch.Tensor, gra
     n, ci, Hi, Wi = img.shape
     Hl, Wl, C1 = Hi // 2, Wi // 2, feat.shape[-1]
     _run("thin_wgrad", 1, 2.0 * feat.numel() * 16 * ci, 4.0 * (feat.numel() + img.numel() + grad.numel()),
-         lambda: _lib.load().mdgan_thin_wgrad(_ptr(feat), _ptr(img), _ptr(partial), n, ci, Hl, Wl, C1, _stream()))
+         lambda: _K.thin_wgrad(feat, img, partial, n, ci, Hl, Wl, C1))
     return reduce_slices(partial, grad, thin_wgrad_slices(n, Hl, Wl))
 
 
@@ -323,31 +342,45 @@ def bn_forward(x, out, gamma, beta, running_mean, running_var, nbt, stats, works
                round_tf32=False, eps=1e-5, momentum=0.1):
     # algorithmic bytes: read x for the statistics, read x + write out for the normalisation
     _run("bn_forward", 2, 0, 4.0 * 3 * G * Pg * Cc,
-         lambda: _lib.load().mdgan_bn_forward(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(running_mean),
-                                              _ptr(running_var), _ptr(nbt), _ptr(stats), _ptr(workspace), _ptr(counters),
-                                              G, Pg, Cc, eps, momentum, act, slope, int(round_tf32), _stream()))
+         lambda: _K.bn_forward(x, out, gamma, beta, running_mean,
+                                              running_var, nbt, stats, workspace, counters,
+                                              G, Pg, Cc, eps, momentum, act, slope, int(round_tf32)))
+    return out
+
+
+def bn_finalize(partial, plan, col_stride, fold, gamma, beta, running_mean, running_var, nbt, stats, G, Pg, Cc,
+                eps=1e-5, momentum=0.1):
+    """Statistics reduced by the producing GEMM (conv_gemm bn_partial; plan from conv_stats_plan) -> stats / running."""
+    row_tiles, tpg, phases = plan
+    _run("bn_forward", 1, 0, 4.0 * 2 * phases * row_tiles * col_stride,
+         lambda: _K.bn_finalize(partial, phases, row_tiles, tpg, col_stride, fold, gamma, beta, running_mean, running_var,
+                                nbt, stats, G, Pg, Cc, eps, momentum))
+
+
+def bn_apply(x, stats, out, G, Pg, Cc, act, slope, round_tf32=False):
+    _run("bn_forward", 1, 0, 4.0 * 2 * G * Pg * Cc,
+         lambda: _K.bn_apply(x, stats, out, G, Pg, Cc, act, slope, int(round_tf32)))
     return out
 
 
 def bn_backward(da, x, stats, dx, dgamma, dbeta, sums, workspace, counters, G, Pg, Cc, act, slope, round_tf32=False):
     # algorithmic bytes: read da + x for the sums, read da + x and write dx for the gradient
     _run("bn_backward", 2, 0, 4.0 * 5 * G * Pg * Cc,
-         lambda: _lib.load().mdgan_bn_backward(_ptr(da), _ptr(x), _ptr(stats), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                                               _ptr(sums), _ptr(workspace), _ptr(counters), G, Pg, Cc, act, slope,
-                                               int(round_tf32), _stream()))
+         lambda: _K.bn_backward(da, x, stats, dx, dgamma, dbeta,
+                                               sums, workspace, counters, G, Pg, Cc, act, slope,
+                                               int(round_tf32)))
     return dx
 
 
 def act_backward(da, a, dz, act, slope, round_tf32=False):
     _run("act_backward", 1, 0, 4.0 * 3 * a.numel(),
-         lambda: _lib.load().mdgan_act_backward(_ptr(da), _ptr(a), _ptr(dz), a.numel(), act, slope, int(round_tf32),
-                                                _stream()))
+         lambda: _K.act_backward(da, a, dz, a.numel(), act, slope, int(round_tf32)))
     return dz
 
 
 def tanh_backward(s, x, out, scale: float):
     _run("tanh_backward", 1, 0, 4.0 * 3 * x.numel(),
-         lambda: _lib.load().mdgan_tanh_backward(_ptr(s), _ptr(x), _ptr(out), x.numel(), scale, _stream()))
+         lambda: _K.tanh_backward(s, x, out, x.numel(), scale))
     return out
 
 
@@ -355,14 +388,14 @@ def tanh_backward_slices(F, x, out, k: int, N: int, scale: float):
     """F [N, b*C*H*W] feedback slices (worker order), x / out [k*b, C, H, W]: group sum per generated batch + tanh'."""
     n_per = x.numel() // k
     _run("tanh_backward", 1, 0, 4.0 * (F.numel() + 2 * x.numel()),
-         lambda: _lib.load().mdgan_tanh_backward_slices(_ptr(F), _ptr(x), _ptr(out), n_per, k, N, scale, _stream()))
+         lambda: _K.tanh_backward_slices(F, x, out, n_per, k, N, scale))
     return out
 
 
 # ----------------------------------------------------------------------------- peer-memory exchange (NVLink)
 def peer_signal(flag_addrs: torch.Tensor, n: int, epoch: torch.Tensor, advance: bool):
     _run("peer_signal", 1, 0, 4.0 * n,
-         lambda: _lib.load().mdgan_peer_signal(_ptr(flag_addrs), n, _ptr(epoch), int(advance), _stream()))
+         lambda: _K.peer_signal(flag_addrs, n, epoch, int(advance)))
 
 
 def peer_timeout_ms() -> int:
@@ -372,34 +405,32 @@ def peer_timeout_ms() -> int:
 
 def peer_wait(flags: torch.Tensor, n: int, epoch: torch.Tensor, advance: bool, err: torch.Tensor):
     _run("peer_wait", 1, 0, 4.0 * n,
-         lambda: _lib.load().mdgan_peer_wait(_ptr(flags), n, _ptr(epoch), int(advance), _ptr(err),
-                                             C.c_longlong(peer_timeout_ms()), _stream()))
+         lambda: _K.peer_wait(flags, n, epoch, int(advance), err, peer_timeout_ms()))
 
 
 def peer_push(src: torch.Tensor, dst_addrs: torch.Tensor, n_dst: int):
     _run("peer_push", 1, 0, 4.0 * src.numel() * (1 + n_dst),
-         lambda: _lib.load().mdgan_peer_push(_ptr(src), _ptr(dst_addrs), n_dst, src.numel(), _stream()))
+         lambda: _K.peer_push(src, dst_addrs, n_dst, src.numel()))
 
 
 # ----------------------------------------------------------------------------- head / loss / optimiser
 def head_pack(w, wt):
     """w PyTorch [1, C, k, k] -> wt [k*k, C] (the NHWC order of the activations)."""
     Cc, HW = w.shape[1], w.shape[2] * w.shape[3]
-    _run("head_pack", 1, 0, 8.0 * w.numel(), lambda: _lib.load().mdgan_head_pack(_ptr(w), _ptr(wt), HW, Cc, _stream()))
+    _run("head_pack", 1, 0, 8.0 * w.numel(), lambda: _K.head_pack(w, wt, HW, Cc))
     return wt
 
 
 def head_forward(a, w, label, prob, loss_terms, dlogit, loss, counter, G, b, HW, Cc):
     """counter: one zero-initialised int32 device scalar (block counter of the fused loss reduction)."""
     _run("head_forward", 1, 2.0 * G * b * HW * Cc, 4.0 * (G * b * HW * Cc + HW * Cc),
-         lambda: _lib.load().mdgan_head_forward(_ptr(a), _ptr(w), _ptr(label), _ptr(prob), _ptr(loss_terms),
-                                                _ptr(dlogit), _ptr(loss), _ptr(counter), G, b, HW, Cc, _stream()))
+         lambda: _K.head_forward(a, w, label, prob, loss_terms,
+                                                dlogit, loss, counter, G, b, HW, Cc))
 
 
 def head_backward(a, w, dlogit, da, dw, n_total, HW, Cc):
     _run("head_backward", 1, 4.0 * n_total * HW * Cc, 4.0 * (2 * n_total * HW * Cc + 2 * HW * Cc),
-         lambda: _lib.load().mdgan_head_backward(_ptr(a), _ptr(w), _ptr(dlogit), _ptr(da), _ptr(dw), n_total, HW, Cc,
-                                                 _stream()))
+         lambda: _K.head_backward(a, w, dlogit, da, dw, n_total, HW, Cc))
 
 
 def adam_step(p, g, m, v, step_count, lr, beta1, beta2, eps=1e-8):
@@ -407,18 +438,18 @@ def adam_step(p, g, m, v, step_count, lr, beta1, beta2, eps=1e-8):
     if step_count.numel() < 2:
         raise _lib.MdganLibraryError("adam_step: step_count must hold 2 int32 (step, block counter)")
     _run("adam_step", 1, 0, 28.0 * p.numel(),
-         lambda: _lib.load().mdgan_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(step_count), lr, beta1,
-                                             beta2, eps, _stream()))
+         lambda: _K.adam_step(p, g, m, v, p.numel(), step_count, lr, beta1,
+                                             beta2, eps))
 
 
 def pad_rows(x, out, round_tf32=False):
     rows, cin = x.shape
     _run("pad_rows", 1, 0, 4.0 * (x.numel() + out.numel()),
-         lambda: _lib.load().mdgan_pad_rows(_ptr(x), _ptr(out), rows, cin, out.shape[1], int(round_tf32), _stream()))
+         lambda: _K.pad_rows(x, out, rows, cin, out.shape[1], int(round_tf32)))
     return out
 
 
 def sum_slices(x, out, count: int, stride: int):
     _run("sum_slices", 1, 0, 4.0 * out.numel() * (count + 1),
-         lambda: _lib.load().mdgan_sum_slices(_ptr(x), _ptr(out), out.numel(), count, stride, _stream()))
+         lambda: _K.sum_slices(x, out, out.numel(), count, stride))
     return out

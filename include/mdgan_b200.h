@@ -70,13 +70,19 @@ int mdgan_pack_weights_multi(const long long* jobs_dev, int n_jobs, int total_bl
  * (actors/server.py:271-297).  force_bn = 0 lets the launcher pick the tile width.  gate (optional, NHWC outputs only,
  * same shape as dst): dst = result * act'(gate), gate_act = MDGAN_ACT_RELU / MDGAN_ACT_LRELU(gate_slope) -- the backward
  * of the activation whose OUTPUT is `gate`, fused into the data-gradient GEMM that feeds it.
+ * bn_partial (optional; tf32x3 precision, plain NHWC outputs only): [phases][row tiles][2][N_pad] floats -- every CTA
+ * also writes the per-column sum and sum of squares of the values it stores (fixed reduction tree), i.e. the train-mode
+ * BatchNorm statistics of the layer without another pass over its output; mdgan_bn_finalize turns them into
+ * mean / invstd / scale / shift + running statistics.  mdgan_conv_rows_per_tile gives the GEMM rows one CTA owns
+ * (row tiles = ceil(n_img*Hg*Wg / rows); 0 = fused statistics unavailable in this mode).
  * Replaces: nn.Conv2d(k4,s2,p1) forward CIFAR10.py:88,92 / CelebA.py:81,85,88; nn.ConvTranspose2d forward
  * CIFAR10.py:118-130 / CelebA.py:113-131 (+ torch.tanh CIFAR10.py:131 / CelebA.py:140); and their data
  * gradients computed by loss.backward() (actors/worker.py:204,227) and torch.autograd.grad (actors/server.py:286). */
 int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img, int Hg, int Wg,
                     int Hs, int Ws, int C, int mode, int N, int N_pad, int out_nchw, int act, int round_tf32,
                     int accumulate, int precision, int force_bn, const float* gate, int gate_act, float gate_slope,
-                    void* stream);
+                    float* bn_partial, void* stream);
+int mdgan_conv_rows_per_tile(int Hg, int Wg, int precision);
 
 /* ---- weight gradient, tcgen05 (kind::tf32, MN-major operands), split-K over pixels ----------------------------
  * partial[split][tap][C1][C2] = sum_p lo[p][c1] * hi[gather(p, tap)][c2]; mode DOWN = 16 taps of the k4 s2 p1
@@ -122,6 +128,18 @@ int mdgan_bn_forward(const float* x, float* out, const float* gamma, const float
                      float* running_var, long long* num_batches_tracked, float* stats, float* workspace,
                      unsigned int* counters, int G, int Pg, int C, float eps, float momentum, int act, float slope,
                      int round_tf32, void* stream);
+/* The two halves of mdgan_bn_forward when the producing GEMM already reduced the statistics (mdgan_conv_gemm's
+ * bn_partial): mdgan_bn_finalize sums, in fp64 and in a fixed order, the partial slices of every pass g -- slices
+ * (phase, tile) with tile in [g*tiles_per_group, (g+1)*tiles_per_group), `fold` column groups of stride C each
+ * (fold = k*k for the generator's first layer, whose GEMM columns are (position, channel); 1 otherwise), slice layout
+ * [2][col_stride] -- and writes stats / running statistics / num_batches_tracked exactly like mdgan_bn_forward;
+ * mdgan_bn_apply is the normalise + activation pass. */
+int mdgan_bn_finalize(const float* partial, int phases, int row_tiles, int tiles_per_group, int col_stride, int fold,
+                      const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      long long* num_batches_tracked, float* stats, int G, int Pg, int C, float eps, float momentum,
+                      void* stream);
+int mdgan_bn_apply(const float* x, const float* stats, float* out, int G, int Pg, int C, int act, float slope,
+                   int round_tf32, void* stream);
 int mdgan_bn_backward(const float* da, const float* x, const float* stats, float* dx, float* dgamma, float* dbeta,
                       float* sums, float* workspace, unsigned int* counters, int G, int Pg, int C, int act, float slope,
                       int round_tf32, void* stream);

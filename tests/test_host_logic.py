@@ -197,3 +197,19 @@ def test_bootstrap_cli_keeps_reference_flags():
         bootstrap.main(["--world_size", "3", "--ranks", "0..2", "--dataset", "CIFAR10", "--device", "cpu"])
     with pytest.raises(ValueError):
         bootstrap.main(["--world_size", "4", "--ranks", "0..3", "--dataset", "CIFAR10", "--device", "cuda"])
+
+
+def test_torch_custom_ops_cover_the_c_abi():
+    """The C-ABI launchers are registered as torch.ops.mdgan_b200.* (CUDA key only: no CPU kernel to fall back to),
+    one op per device-side launcher of the header, argument for argument."""
+    from mdgan_b200 import _lib, torch_ops
+
+    host_only = {"mdgan_abi_version", "mdgan_check_device", "mdgan_wgrad_splits", "mdgan_pack_job_words",
+                 "mdgan_bn_workspace_floats", "mdgan_thin_wgrad_slices", "mdgan_conv_rows_per_tile"}
+    assert {f"mdgan_{n}" for n in torch_ops.SPECS} == set(_lib.SIGNATURES) - host_only
+    for name, spec in torch_ops.SPECS.items():
+        op = getattr(torch.ops.mdgan_b200, name).default
+        assert len(op._schema.arguments) + 1 == len(_lib.SIGNATURES[f"mdgan_{name}"][1])   # + the stream
+        assert any(a.alias_info is not None and a.alias_info.is_write for a in op._schema.arguments), name
+    with pytest.raises(NotImplementedError):
+        torch.ops.mdgan_b200.pad_rows(torch.zeros(4, 4), torch.zeros(4, 8), 4, 4, 8, 0)
