@@ -256,7 +256,7 @@ def reference_cpu(args, n_workers: int, steps: int, warmup: int, budget_s: float
                 return {"ms_per_step": r["ms_per_step"], "steps": r["steps"], "warmup": r["warmup"], "cores": cores,
                         "kind": "reference", "phases_ms": r["phases_ms"],
                         "sample": (f"{r['steps']} generator iterations of the same workload (K={n_workers}, b={args.batch}) "
-                                   f"after {r['warmup']} warm-up, UNMODIFIED reference bootstrap.py --backend gloo --device cpu: "
+                                   f"after {r['warmup']} warm-up, UNMODIFIED reference actors ({r['launcher']}) --backend gloo --device cpu: "
                                    f"{r['processes']} processes x {r['threads_per_process']} OMP threads on {cores} cores, server "
                                    "CSV end.epoch_calculation - start.epoch_calculation")}
             note = "oracle/_ref is not installed on this host"

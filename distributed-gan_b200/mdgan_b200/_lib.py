@@ -20,10 +20,13 @@ _ll = C.c_longlong
 SIGNATURES = {
     "mdgan_abi_version": (_i, []),
     "mdgan_check_device": (_i, []),
-    "mdgan_conv_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _f, _p, _p]),
+    "mdgan_conv_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _f, _p, _p, _p, _i, _f, _i, _p]),
     "mdgan_conv_rows_per_tile": (_i, [_i, _i, _i]),
+    "mdgan_conv_stat_phases": (_i, [_i, _i, _i, _i, _i]),
     "mdgan_bn_finalize": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _p]),
     "mdgan_bn_apply": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
+    "mdgan_bn_bwd_finalize": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p]),
+    "mdgan_bn_bwd_apply_dy": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "mdgan_wgrad_splits": (_i, [_i, _i, _i, _i, _i, _i]),
     "mdgan_wgrad_gemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_pack_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
@@ -45,6 +48,7 @@ SIGNATURES = {
     "mdgan_peer_signal": (_i, [_p, _i, _p, _i, _p]),
     "mdgan_peer_wait": (_i, [_p, _i, _p, _i, _p, _ll, _p]),
     "mdgan_peer_push": (_i, [_p, _p, _i, _ll, _p]),
+    "mdgan_peer_push_multicast": (_i, [_p, _p, _ll, _p]),
     "mdgan_tanh_backward_slices": (_i, [_p, _p, _p, _ll, _i, _i, _f, _p]),
     "mdgan_thin_down": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "mdgan_thin_up": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

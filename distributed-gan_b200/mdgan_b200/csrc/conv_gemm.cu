@@ -55,6 +55,15 @@ struct ConvGemmParams {
   float gate_slope;
   float* bn_partial;  // optional [phases][row tiles][2][N_pad]: per-CTA column sums / sums of squares of the stored
                       //   values (the BatchNorm statistics of the layer, finalized by mdgan_bn_finalize)
+  // BatchNorm-backward fusion (data-gradient GEMMs whose output is the gradient da of a BatchNorm+activation output):
+  // with bnb_z (the BatchNorm INPUT, NHWC like dst) and bnb_stats ([groups][4][N]: mean, invstd, scale, shift) the
+  // epilogue stores dy = da * act'(z*scale + shift) instead of da and bn_partial receives the column sums of dy and
+  // of dy * xhat (xhat = (z - mean) * invstd): the reduction pass of the BatchNorm backward.
+  const float* bnb_z;
+  const float* bnb_stats;
+  int bnb_act;
+  float bnb_slope;
+  int bnb_rows_per_group;  // GEMM rows (low-resolution positions) per BatchNorm pass; a CTA never straddles two
 };
 
 constexpr int kBM = 128;
@@ -161,8 +170,34 @@ __device__ __forceinline__ void conv_epilogue(const ConvGemmParams& p, uint32_t 
         }
         if (STATS && p.bn_partial != nullptr) {  // warp-uniform: every lane takes part in the shuffles
           float s1[16], s2[16];
+          if (p.bnb_z != nullptr) {
+            // dy = da * act'(y) and dy * xhat from the BatchNorm input z at the same NHWC position (N % 16 == 0)
+            const float* st = p.bnb_stats + static_cast<size_t>(m0 / p.bnb_rows_per_group) * 4 * p.N + nbase;
+            const float* zr = p.bnb_z + (static_cast<size_t>((img * Ho + oh) * Wo + ow)) * p.N + nbase;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { s1[j] = ok ? v[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+            for (int j = 0; j < 16; j += 4) {
+              const float4 z4 = ok ? __ldg(reinterpret_cast<const float4*>(zr + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 mean = __ldg(reinterpret_cast<const float4*>(st + j));
+              const float4 istd = __ldg(reinterpret_cast<const float4*>(st + p.N + j));
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(st + 2 * p.N + j));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(st + 3 * p.N + j));
+              const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, mm4[4] = {mean.x, mean.y, mean.z, mean.w};
+              const float ii[4] = {istd.x, istd.y, istd.z, istd.w}, cc[4] = {sc.x, sc.y, sc.z, sc.w};
+              const float hh[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float y = fmaf(zz[t], cc[t], hh[t]);
+                const float g = y > 0.f ? 1.f : (p.bnb_act == 2 ? p.bnb_slope : (p.bnb_act == 1 ? 0.f : 1.f));
+                const float dy = ok ? v[j + t] * g : 0.f;
+                v[j + t] = dy;
+                s1[j + t] = dy;
+                s2[j + t] = dy * ((zz[t] - mm4[t]) * ii[t]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { s1[j] = ok ? v[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+          }
           warp_column_sums16(s1, lane);
           warp_column_sums16(s2, lane);
           if ((lane & 1) == 0) {
@@ -404,10 +439,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
 //   warps 4-11 : loaders (global -> registers kPrefetch K steps ahead -> raw fp32 stage), then the epilogue
 //   warp  12   : B producer (TMA, hi + lo)        warp 13: TMEM allocator + single-thread MMA issuer
 //   warp  14   : (TMA_A only) activation-tile TMA issuer
-// With the TMA-fed activation tile the loader warps have nothing to load, so TG groups of four transposer warps
-// (warps 4g..4g+3, group g takes K steps g, g+TG, ...) work on consecutive K steps concurrently: one group's chain
-// (wait raw -> 8 LDS.128 -> split -> wait TMEM stage -> 2 tcgen05.st -> wait::st -> arrive) is ~1200 clk long and
-// was what paced a K step, not the tensor pipe (64-wide tiles: 552 clk of MMA per K step).
+// With the TMA-fed activation tile the loader warps have nothing to load, so TG = 2 lets warps 4-7 act as a second
+// transposer group (group g takes K steps g, g+2, ...).  Measured: no effect (see conv_tg()), the option is kept for the
+// cross-variant bit-identity stress (tools/stress_conv.py).
 constexpr int kTaThreads = (4 + kNumProducerWarps + 2) * 32;
 constexpr int kTaThreadsTma = kTaThreads + 32;
 
@@ -442,7 +476,13 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // one tap x 32 channels, element strides = the conv stride, out-of-bounds = zero padding) instead of by the eight
 // loader warps: the tile then crosses the L1/shared-memory arrays once (the TMA write) instead of three times
 // (L1 fill, L1 read, shared store).  Possible whenever 128 consecutive rows of the (n, i, j) grid form a box.
-template <int BN, bool TMA_A, int TG>
+// UP2 (BN = 128, UP mode with 64 output channels): one CTA computes BOTH column parities (pw = 0, 1) of output-row parity
+// ph = blockIdx.z.  The two parities read the same source rows and overlapping source columns: the six shifted
+// activation tiles (dh in {ph-1, ph}) x (dw in {0, -1, +1}) replace the 2 x 4 tiles of two single-phase CTAs, the dw = 0
+// tile feeds both parities with ONE 128-wide MMA per K slice ([pw0 | pw1] weights side by side, accumulators side by
+// side in TMEM), the dw = -1 / +1 tiles feed pw = 0 / 1 with 64-wide MMAs.  Per K slice: 64 + 46 + 46 clk of MMA instead
+// of 4 x 46, 25 % less transposer work, half as many CTAs with 24 instead of 16 K steps each.
+template <int BN, bool TMA_A, int TG, bool UP2 = false>
 __global__ void __launch_bounds__(TMA_A ? kTaThreadsTma : kTaThreads, 1)
 conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
                     const ConvGemmParams p) {
@@ -463,11 +503,12 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * p.rows_per_tile;
   const int n0 = blockIdx.y * BN;
+  static_assert(!UP2 || (BN == 128 && TMA_A), "UP2 pairs two 64-wide phases in the 128-wide TMA-fed kernel");
   const int phase = blockIdx.z;
-  const int ph = phase >> 1, pw = phase & 1;
+  const int ph = UP2 ? phase : phase >> 1, pw = phase & 1;
   const int taps = (p.mode == 0) ? 16 : (p.mode == 1 ? 4 : 1);
   const int cchunks = p.C / kBK;
-  const int ksteps = taps * cchunks;
+  const int ksteps = UP2 ? 6 * cchunks : taps * cchunks;
 
   pdl_trigger();
   if (threadIdx.x == 0) {
@@ -486,7 +527,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
 
-  static_assert(TG >= 1 && TG <= 3 && (TMA_A || TG == 1), "transposer groups: the loader warps double as transposers only when TMA feeds the tile");
+  static_assert(TG >= 1 && TG <= 2 && (TMA_A || TG == 1), "transposer groups: the loader warps double as transposers only when TMA feeds the tile");
   if (warp < 12) {
     if (warp < 4 * TG) {
       // ---------------------------------------------------------------- transposers: raw stage -> TMEM A stage
@@ -587,7 +628,11 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
       __syncwarp();
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after_sync();
-      conv_epilogue<BN, S::kAccs, true>(p, tmem_base, warp & 3, (warp - 4) >> 2, lane, m0, n0, ph, pw, red);
+      if (UP2)  // columns [64 half, 64 half + 64) are the 64 channels of column parity pw = half
+        conv_epilogue<BN, S::kAccs, true>(p, tmem_base, warp & 3, (warp - 4) >> 2, lane, m0, -64 * ((warp - 4) >> 2), ph,
+                                          (warp - 4) >> 2, red);
+      else
+        conv_epilogue<BN, S::kAccs, true>(p, tmem_base, warp & 3, (warp - 4) >> 2, lane, m0, n0, ph, pw, red);
       tc_fence_before_sync();
     }
   } else if (TMA_A && warp == 14) {
@@ -600,7 +645,8 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
       uint32_t par = 0;
       for (int it = 0; it < ksteps; ++it) {
         int dh, dw;
-        if (p.mode == 0) { dh = (tap_l >> 2) - 1; dw = (tap_l & 3) - 1; }
+        if (UP2) { dh = ph - tap_l / 3; const int j = tap_l % 3; dw = j == 0 ? 0 : (j == 1 ? -1 : 1); }  // tap_l = 3 a + j
+        else if (p.mode == 0) { dh = (tap_l >> 2) - 1; dw = (tap_l & 3) - 1; }
         else if (p.mode == 1) { dh = ph - (tap_l >> 1); dw = pw - (tap_l & 1); }
         else { dh = 0; dw = 0; }
         mbar_wait(&raw_empty[s], par ^ 1);
@@ -616,12 +662,30 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
       const int row0 = (p.mode == 1 ? phase * p.N_pad : 0) + n0;
       int s = 0;
       uint32_t par = 0;
+      int tap_l = 0, cc_l = 0;  // UP2 only
       for (int it = 0; it < ksteps; ++it) {
         mbar_wait(&b_empty[s], par ^ 1);
-        mbar_arrive_expect_tx(&b_full[s], S::kBStageBytes);
         const uint32_t b_dst = smem_u32(smem + S::kBOff + s * S::kBStageBytes);
-        tma_load_2d(b_dst, &tmap_w, &b_full[s], it * kBK, row0);
-        tma_load_2d(b_dst + S::kBBytes, &tmap_w, &b_full[s], it * kBK, row0 + p.lo_row_offset);
+        if (UP2) {
+          // packed weights: row (2 ph + pw) * 64 + n, column (2 a + b) * C + c; tile rows 0-63 = pw 0, 64-127 = pw 1
+          const int a = tap_l / 3, j = tap_l % 3;
+          const int r0 = (2 * ph) * 64, r1 = (2 * ph + 1) * 64;
+          const int k0 = (2 * a) * p.C + cc_l * kBK, k1 = (2 * a + 1) * p.C + cc_l * kBK;
+          mbar_arrive_expect_tx(&b_full[s], j == 0 ? 4 * 64 * 128 : 2 * 64 * 128);
+          if (j == 0 || j == 1) {   // pw = 0: b = 0 (dw = 0) or b = 1 (dw = -1)
+            tma_load_2d(b_dst, &tmap_w, &b_full[s], j == 0 ? k0 : k1, r0);
+            tma_load_2d(b_dst + S::kBBytes, &tmap_w, &b_full[s], j == 0 ? k0 : k1, r0 + p.lo_row_offset);
+          }
+          if (j == 0 || j == 2) {   // pw = 1: b = 1 (dw = 0) or b = 0 (dw = +1)
+            tma_load_2d(b_dst + 64 * 128, &tmap_w, &b_full[s], j == 0 ? k1 : k0, r1);
+            tma_load_2d(b_dst + S::kBBytes + 64 * 128, &tmap_w, &b_full[s], j == 0 ? k1 : k0, r1 + p.lo_row_offset);
+          }
+          if (++cc_l == cchunks) { cc_l = 0; ++tap_l; }
+        } else {
+          mbar_arrive_expect_tx(&b_full[s], S::kBStageBytes);
+          tma_load_2d(b_dst, &tmap_w, &b_full[s], it * kBK, row0);
+          tma_load_2d(b_dst + S::kBBytes, &tmap_w, &b_full[s], it * kBK, row0 + p.lo_row_offset);
+        }
         if (++s == S::kBStages) { s = 0; par ^= 1; }
       }
     }
@@ -635,19 +699,29 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
       int sb = 0, t = 0;
       uint32_t parb = 0, part = 0;
       uint64_t db0 = bdesc0;
+      int tap_l = 0, cc_l = 0;  // UP2 only
       for (int it = 0; it < ksteps; ++it) {
         mbar_wait(&a_full[t], part);
         mbar_wait(&b_full[sb], parb);
         tc_fence_after_sync();
-        const uint32_t acc = it != 0 ? 1u : 0u;
+        const uint32_t acc = it != 0 ? 1u : 0u;   // UP2: step 0 is a dw = 0 tile, which writes all 128 columns
         const uint32_t a_hi0 = tmem_base + S::kACol0 + t * 64;
+        // UP2: dw = 0 -> one 128-wide MMA over [pw 0 | pw 1]; dw = -1 -> 64-wide on the left half; +1 -> right half
+        uint32_t idesc_s = idesc, col_off = 0;
+        uint64_t db_off = 0;
+        if (UP2) {
+          const int j = tap_l % 3;
+          if (j != 0) idesc_s = make_idesc_tf32(kBM, 64, 0, 0);
+          if (j == 2) { col_off = 64; db_off = (64 * 128) >> 4; }
+          if (++cc_l == cchunks) { cc_l = 0; ++tap_l; }
+        }
 #pragma unroll
         for (int k = 0; k < kBK / 8; ++k) {
           const uint32_t a_hi = a_hi0 + 8 * k, a_lo = a_hi + 32;
-          const uint64_t db = db0 + 2 * k;
-          umma_tf32_ts(acc_corr, a_lo, db, idesc, k == 0 ? acc : 1u);
-          umma_tf32_ts(acc_corr, a_hi, db + kLoStep, idesc, 1u);
-          umma_tf32_ts(tmem_base + (k % S::kMain) * BN, a_hi, db, idesc, k < S::kMain ? acc : 1u);
+          const uint64_t db = db0 + db_off + 2 * k;
+          umma_tf32_ts(acc_corr + col_off, a_lo, db, idesc_s, k == 0 ? acc : 1u);
+          umma_tf32_ts(acc_corr + col_off, a_hi, db + kLoStep, idesc_s, 1u);
+          umma_tf32_ts(tmem_base + (k % S::kMain) * BN + col_off, a_hi, db, idesc_s, k < S::kMain ? acc : 1u);
         }
         umma_commit(&a_empty[t]);
         umma_commit(&b_empty[sb]);
@@ -667,9 +741,17 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   if (p.bn_partial != nullptr && threadIdx.x < 2 * BN) {
     // fused BatchNorm statistics: the CTA's column sums (quarters added in a fixed order) -> its partial slice
     const int stat = threadIdx.x / BN, col = threadIdx.x - stat * BN;
-    const float t = (red[(0 * 2 + stat) * BN + col] + red[(1 * 2 + stat) * BN + col]) +
-                    (red[(2 * 2 + stat) * BN + col] + red[(3 * 2 + stat) * BN + col]);
-    p.bn_partial[((static_cast<size_t>(phase) * gridDim.x + blockIdx.x) * 2 + stat) * p.N_pad + n0 + col] = t;
+    float t = (red[(0 * 2 + stat) * BN + col] + red[(1 * 2 + stat) * BN + col]) +
+              (red[(2 * 2 + stat) * BN + col] + red[(3 * 2 + stat) * BN + col]);
+    if (UP2) {  // columns c and 64 + c are channel c of the two column parities: one slice entry per channel
+      if (col < 64) {
+        t += (red[(0 * 2 + stat) * BN + col + 64] + red[(1 * 2 + stat) * BN + col + 64]) +
+             (red[(2 * 2 + stat) * BN + col + 64] + red[(3 * 2 + stat) * BN + col + 64]);
+        p.bn_partial[((static_cast<size_t>(phase) * gridDim.x + blockIdx.x) * 2 + stat) * p.N_pad + col] = t;
+      }
+    } else {
+      p.bn_partial[((static_cast<size_t>(phase) * gridDim.x + blockIdx.x) * 2 + stat) * p.N_pad + n0 + col] = t;
+    }
   }
 }
 
@@ -684,24 +766,46 @@ static int launch_conv_gemm_ta(const CUtensorMap& tmap, const CUtensorMap& tmap_
   return 0;
 }
 
-// MDGAN_CONV_TG = 1 | 2 | 3 (default 2): groups of transposer warps of the TMA-fed kernel (see conv_gemm_ta_kernel).
+// MDGAN_CONV_TG = 1 (default) | 2: groups of transposer warps of the TMA-fed kernel (see conv_gemm_ta_kernel).  Measured
+// on B200 (round 2, gpurun_out/r2c1_convbench_tg*.log): 1 and 2 groups give the same kernel times to within 1 % on every
+// layer shape and bit-identical results -- the K step is paced by the shared-memory port, not by the transposer chain --
+// so the default stays at the single group.
 static int conv_tg() {
   static const int tg = [] {
     const char* e = getenv("MDGAN_CONV_TG");
-    const int v = e ? atoi(e) : 2;
-    return v < 1 ? 1 : (v > 3 ? 3 : v);
+    const int v = e ? atoi(e) : 1;
+    return v < 1 ? 1 : (v > 2 ? 2 : v);
   }();
   return tg;
+}
+
+// MDGAN_CONV_UP2 = 1 (default) | 0: UP-mode layers with 64 output channels pair their column parities in one CTA.
+static bool conv_up2_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MDGAN_CONV_UP2");
+    return e ? e[0] != '0' : true;
+  }();
+  return on;
+}
+
+static int launch_conv_gemm_up2(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p, dim3 grid,
+                                cudaStream_t st) {
+  using S = ConvTaSmem<128>;
+  if (conv_tg() == 1) {
+    MDGAN_CUDA(configure_smem_once(conv_gemm_ta_kernel<128, true, 1, true>, S::kDynamic));
+    MDGAN_LAUNCH((conv_gemm_ta_kernel<128, true, 1, true>), grid, dim3(kTaThreadsTma), S::kDynamic, st, tmap, tmap_a, p);
+  } else {
+    MDGAN_CUDA(configure_smem_once(conv_gemm_ta_kernel<128, true, 2, true>, S::kDynamic));
+    MDGAN_LAUNCH((conv_gemm_ta_kernel<128, true, 2, true>), grid, dim3(kTaThreadsTma), S::kDynamic, st, tmap, tmap_a, p);
+  }
+  return 0;
 }
 
 template <int BN>
 static int launch_conv_gemm_ta_tma(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p, dim3 grid,
                                    cudaStream_t st) {
-  switch (conv_tg()) {
-    case 1: return launch_conv_gemm_ta<BN, true, 1>(tmap, tmap_a, p, grid, st);
-    case 2: return launch_conv_gemm_ta<BN, true, 2>(tmap, tmap_a, p, grid, st);
-    default: return launch_conv_gemm_ta<BN, true, 3>(tmap, tmap_a, p, grid, st);
-  }
+  return conv_tg() == 1 ? launch_conv_gemm_ta<BN, true, 1>(tmap, tmap_a, p, grid, st)
+                        : launch_conv_gemm_ta<BN, true, 2>(tmap, tmap_a, p, grid, st);
 }
 
 // MDGAN_CONV_TMA_PARTIAL = 1 (default) | 0: also use TMA boxes of whole images that do not fill 128 rows (7x7 grids).
@@ -766,6 +870,20 @@ static int conv_row_tiling(int Hg, int Wg, int precision, int* bn_img, int* bh, 
   return kBM;
 }
 
+// true when mdgan_conv_gemm runs this problem with the paired-parity kernel (conv_gemm_ta_kernel<..., UP2>)
+static bool conv_uses_up2(int mode, int N_pad, int Hg, int Wg, int precision) {
+  if (mode != 1 || N_pad != 64 || precision != 1 || !conv_ta_enabled() || !conv_up2_enabled()) return false;
+  int a, b, c;
+  conv_row_tiling(Hg, Wg, precision, &a, &b, &c);
+  return a > 0;  // TMA-fed activation tile
+}
+
+// Number of phase slices the fused statistics of this problem have (bn_partial is [phases][row tiles][2][N_pad]).
+extern "C" int mdgan_conv_stat_phases(int mode, int N_pad, int Hg, int Wg, int precision) {
+  if (mode != 1) return 1;
+  return conv_uses_up2(mode, N_pad, Hg, Wg, precision) ? 2 : 4;
+}
+
 // GEMM rows one CTA of mdgan_conv_gemm owns for this row grid (callers size the fused-statistics buffer with it:
 // row tiles = ceil(n_img*Hg*Wg / rows)), or 0 when the fused BatchNorm statistics are not available in this mode.
 extern "C" int mdgan_conv_rows_per_tile(int Hg, int Wg, int precision) {
@@ -777,9 +895,12 @@ extern "C" int mdgan_conv_rows_per_tile(int Hg, int Wg, int precision) {
 extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img,
                                int Hg, int Wg, int Hs, int Ws, int C, int mode, int N, int N_pad, int out_nchw,
                                int act, int round_tf32, int accumulate, int precision, int force_bn, const float* gate,
-                               int gate_act, float gate_slope, float* bn_partial, void* stream) {
+                               int gate_act, float gate_slope, float* bn_partial, const float* bnb_z,
+                               const float* bnb_stats, int bnb_act, float bnb_slope, int bnb_groups, void* stream) {
   if (!src || !wpacked || !dst) return MDGAN_ERR_BAD_ARG;
   if (bn_partial && (precision != 1 || !conv_ta_enabled() || out_nchw || gate || act != 0 || accumulate))
+    return MDGAN_ERR_UNSUPPORTED;
+  if (bnb_z && (!bn_partial || !bnb_stats || bias || round_tf32 || N % 16 != 0 || bnb_groups < 1 || bnb_act < 0 || bnb_act > 2))
     return MDGAN_ERR_UNSUPPORTED;
   if (gate && (out_nchw || (gate_act != 1 && gate_act != 2))) return MDGAN_ERR_UNSUPPORTED;
   if (C <= 0 || C % kBK != 0 || mode < 0 || mode > 2) return MDGAN_ERR_UNSUPPORTED;
@@ -793,6 +914,9 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   p.accumulate = accumulate;
   p.gate = gate; p.gate_act = gate_act; p.gate_slope = gate_slope;
   p.bn_partial = bn_partial;
+  p.bnb_z = bnb_z; p.bnb_stats = bnb_stats; p.bnb_act = bnb_act; p.bnb_slope = bnb_slope;
+  p.bnb_rows_per_group = bnb_z ? p.M / bnb_groups : p.M;
+  if (bnb_z && (p.M % bnb_groups != 0)) return MDGAN_ERR_UNSUPPORTED;
   if (accumulate && !out_nchw) return MDGAN_ERR_UNSUPPORTED;
   if (p.M <= 0) return MDGAN_ERR_BAD_ARG;
   const int taps = mode == 0 ? 16 : (mode == 1 ? 4 : 1);
@@ -803,6 +927,7 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   int bn_img = 0, bh = 0, bw = 0;
   p.rows_per_tile = conv_row_tiling(Hg, Wg, precision, &bn_img, &bh, &bw);
   const int row_tiles = ceil_div(p.M, p.rows_per_tile);
+  if (bnb_z && p.bnb_rows_per_group % p.rows_per_tile != 0) return MDGAN_ERR_UNSUPPORTED;  // a CTA must not straddle passes
   const bool x3 = precision == 1;
   // Tile width: the candidate (dividing N_pad) with the lowest estimated time -- wide tiles use the tensor core
   // better, narrow ones fill the 148 SMs when the row grid is small.
@@ -819,11 +944,19 @@ extern "C" int mdgan_conv_gemm(const float* src, const float* wpacked, float* ds
   }
   const uint64_t rows = static_cast<uint64_t>(N_pad) * phases;
   p.lo_row_offset = static_cast<int>(rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (force_bn == 0 && conv_uses_up2(mode, N_pad, Hg, Wg, precision)) {
+    CUtensorMap tmap, tmap_a;
+    int rc = get_tmap_2d_f32(wpacked, rows * 2, static_cast<uint64_t>(taps) * C, 64, &tmap);
+    if (rc != 0) return rc;
+    rc = get_tmap_im2col_f32(src, n_img, Hs, Ws, C, bn_img, bh, bw, 1, &tmap_a);
+    if (rc != 0) return rc;
+    return launch_conv_gemm_up2(tmap, tmap_a, p, dim3(row_tiles, 1, 2), st);
+  }
   CUtensorMap tmap;
   int rc = get_tmap_2d_f32(wpacked, rows * (x3 ? 2 : 1), static_cast<uint64_t>(taps) * C, bn, &tmap);
   if (rc != 0) return rc;
   dim3 grid(row_tiles, N_pad / bn, phases);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x3 && conv_ta_enabled()) {
     CUtensorMap tmap_a = tmap;
     bool tma_a = bn_img > 0;

@@ -149,6 +149,34 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ partial, float* __
   grad[idx] = acc;
 }
 
+// Tiled form of mode 0 (C2 % 32 == 0): a block owns one c1 and 32 consecutive c2; it reads the sixteen tap rows of every
+// split as 128-byte runs (summing the splits in order), transposes through shared memory and writes the 512 gradient
+// words grad[c1][c2_0 .. c2_0+32)[16 taps], which are contiguous.  The element-wise kernel above reads with a stride of
+// one tap slice between neighbouring threads (eight-fold sector amplification).
+__global__ void __launch_bounds__(256) wgrad_unpack_tiled_kernel(const float* __restrict__ partial, float* __restrict__ grad,
+                                                                 int splits, int C1, int C1p, int C2) {
+  __shared__ float tile[16][33];
+  pdl_enter();
+  const int chunks = C2 >> 5;
+  const int c1 = blockIdx.x / chunks, c2_0 = (blockIdx.x - c1 * chunks) << 5;
+  const long long slice = 16LL * C1p * C2;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int tap = (threadIdx.x >> 5) + 8 * r, cl = threadIdx.x & 31;
+    const float* src = partial + ((long long)tap * C1p + c1) * C2 + c2_0 + cl;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += src[s * slice];
+    tile[tap][cl] = acc;
+  }
+  __syncthreads();
+  float* dst = grad + ((long long)c1 * C2 + c2_0) * 16;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int e = threadIdx.x + 256 * r;
+    dst[e] = tile[e & 15][e >> 4];
+  }
+}
+
 // out[i] = sum_s partial[s][i].  Block = 32 outputs x 8 slice lanes (fixed summation order: lane-strided partial sums,
 // then lanes 0..7), so a few hundred slices of a small tensor are read with 8-way parallelism per output.
 __global__ void __launch_bounds__(256) reduce_slices_kernel(const float* __restrict__ partial, float* __restrict__ out,
@@ -457,6 +485,71 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ da, const float* _
   *reinterpret_cast<float4*>(dx + e) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// Backward twin of bn_finalize_kernel: partial slices hold the column sums of dy and of dy * xhat reduced by the
+// data-gradient GEMM that produced dy (mdgan_conv_gemm, bnb_*).  sums[g][2][C] per pass, dgamma / dbeta over all passes.
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int phases, int row_tiles, int tiles_per_group, int col_stride,
+                       float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int C) {
+  pdl_enter();
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const int per_group = phases * tiles_per_group;
+  double tg = 0.0, tb = 0.0;
+  for (int g = 0; g < G; ++g) {
+    double sum = 0.0, sq = 0.0;
+    for (int i = lane; i < per_group; i += 32) {
+      const int t = i % tiles_per_group, ph = i / tiles_per_group;
+      const float* sl = partial + (static_cast<long long>(ph) * row_tiles + g * tiles_per_group + t) * 2 * col_stride + c;
+      sum += __ldcg(sl);
+      sq += __ldcg(sl + col_stride);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+      sums[(long long)g * 2 * C + c] = (float)sum;
+      sums[(long long)g * 2 * C + C + c] = (float)sq;
+    }
+    tb += sum;
+    tg += sq;
+  }
+  if (lane == 0) {
+    if (dgamma) dgamma[c] = (float)tg;
+    if (dbeta) dbeta[c] = (float)tb;
+  }
+}
+
+// dx = scale * (dy - mean(dy) - xhat * mean(dy * xhat)) with dy already gated by the activation (see above)
+__global__ void bn_bwd_apply_dy_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                       const float* __restrict__ stats, const float* __restrict__ sums,
+                                       float* __restrict__ dx, int Pg, int C, long long total4, int round_tf32) {
+  pdl_enter();
+  long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const long long e = i4 * 4;
+  const int c = e % C;
+  const int g = (e / C) / Pg;
+  const float* st = stats + (long long)g * 4 * C + c;
+  const float* sm = sums + (long long)g * 2 * C + c;
+  const float4 xv = *reinterpret_cast<const float4*>(x + e);
+  const float4 dv = *reinterpret_cast<const float4*>(dy + e);
+  const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+  const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+  float o[4];
+  const float invP = 1.f / (float)Pg;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float mean = st[j], invstd = st[C + j], sc = st[2 * C + j];
+    const float xhat = (xs[j] - mean) * invstd;
+    o[j] = sc * (ds[j] - sm[j] * invP - xhat * (sm[C + j] * invP));
+    if (round_tf32) o[j] = to_tf32(o[j]);
+  }
+  *reinterpret_cast<float4*>(dx + e) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 // dz = da * act'(a) for an activation with no BatchNorm in front (a = act(z); sign(a) == sign(z) for slope > 0).
 __global__ void act_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a, float* __restrict__ dz,
                                long long total4, int act, float slope, int round_tf32) {
@@ -693,6 +786,11 @@ extern "C" int mdgan_wgrad_unpack(const float* partial, float* grad, int mode, i
   if (!partial || !grad || (mode != 0 && mode != 2)) return MDGAN_ERR_BAD_ARG;
   const int taps = mode == 0 ? 16 : 1;
   const long long total = mode == 0 ? (long long)C1 * C2 * 16 : (long long)C1 * N * KK;
+  if (mode == 0 && C2 % 32 == 0) {
+    MDGAN_LAUNCH(wgrad_unpack_tiled_kernel, dim3((unsigned)(C1 * (C2 / 32))), dim3(256), 0, (cudaStream_t)stream, partial,
+                 grad, splits, C1, C1p, C2);
+    return 0;
+  }
   MDGAN_LAUNCH(wgrad_unpack_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, partial, grad, mode,
                splits, taps, C1, C1p, C2, N, KK, total);
   return 0;
@@ -775,6 +873,26 @@ extern "C" int mdgan_bn_backward(const float* da, const float* x, const float* s
   const long long total4 = (long long)G * Pg * C / 4;
   MDGAN_LAUNCH(bn_bwd_apply_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, da, x, stats, sums, dx, Pg, C, total4,
                act, slope, round_tf32);
+  return 0;
+}
+
+extern "C" int mdgan_bn_bwd_finalize(const float* partial, int phases, int row_tiles, int tiles_per_group, int col_stride,
+                                     float* sums, float* dgamma, float* dbeta, int G, int C, void* stream) {
+  if (!partial || !sums) return MDGAN_ERR_BAD_ARG;
+  if (C % 8 != 0 || G < 1 || phases < 1 || tiles_per_group < 1 || G * tiles_per_group > row_tiles || C > col_stride)
+    return MDGAN_ERR_UNSUPPORTED;
+  MDGAN_LAUNCH(bn_bwd_finalize_kernel, dim3(C / 8), dim3(256), 0, (cudaStream_t)stream, partial, phases, row_tiles,
+               tiles_per_group, col_stride, sums, dgamma, dbeta, G, C);
+  return 0;
+}
+
+extern "C" int mdgan_bn_bwd_apply_dy(const float* dy, const float* x, const float* stats, const float* sums, float* dx,
+                                     int G, int Pg, int C, int round_tf32, void* stream) {
+  if (!dy || !x || !stats || !sums || !dx) return MDGAN_ERR_BAD_ARG;
+  if (C % 4 != 0 || G < 1 || Pg < 1) return MDGAN_ERR_UNSUPPORTED;
+  const long long total4 = (long long)G * Pg * C / 4;
+  MDGAN_LAUNCH(bn_bwd_apply_dy_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, (cudaStream_t)stream, dy, x, stats, sums,
+               dx, Pg, C, total4, round_tf32);
   return 0;
 }
 

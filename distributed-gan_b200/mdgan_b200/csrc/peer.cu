@@ -74,6 +74,20 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const float* __restrict_
   }
 }
 
+// mc[i] = src[i] through the NVSwitch multicast mapping of the symmetric buffer: ONE store per element leaves this GPU
+// and the switch replicates it into every process' copy (the local one included), instead of one store per peer --
+// the generated batch crosses GPU 0's NVLink ports once, not (N - 1) times.
+__global__ void __launch_bounds__(256) peer_push_mc_kernel(const float* __restrict__ src, float* mc, long long n4) {
+  pdl_enter();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<float4*>(mc) + i),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+}
+
 // out[s*n_per + j] = scale * (1 - x^2) * sum_{n = s, s+k, ... < N} F[n*n_per + j]: the group sum of the workers'
 // feedbacks that share generated batch s (ascending worker order, fixed), fused with the generator's tanh backward.
 __global__ void tanh_bwd_slices_kernel(const float* __restrict__ F, const float* __restrict__ x, float* __restrict__ out,
@@ -124,6 +138,14 @@ extern "C" int mdgan_peer_push(const float* src, const unsigned long long* dst_a
   if (blocks > 148 * 4) blocks = 148 * 4;
   MDGAN_LAUNCH(peer_push_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, src, dst_addrs_dev, n_dst,
                n / 4);
+  return 0;
+}
+
+extern "C" int mdgan_peer_push_multicast(const float* src, float* mc_dst, long long n, void* stream) {
+  if (!src || !mc_dst || n % 4 != 0) return MDGAN_ERR_BAD_ARG;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  MDGAN_LAUNCH(peer_push_mc_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, src, mc_dst, n / 4);
   return 0;
 }
 

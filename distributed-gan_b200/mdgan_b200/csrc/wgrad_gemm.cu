@@ -540,11 +540,12 @@ static int launch_wgrad_ta_tg(const CUtensorMap& tmap_lo, const WgradParams& p, 
   return 0;
 }
 
-// MDGAN_WGRAD_TG = 1 | 2 (default 2): groups of transposer warps (see wgrad_gemm_ta_kernel).
+// MDGAN_WGRAD_TG = 1 (default) | 2: groups of transposer warps (see wgrad_gemm_ta_kernel).  Measured on B200 (round 2):
+// no difference in kernel time, bit-identical results; the default stays at one group.
 static int wgrad_tg() {
   static const int tg = [] {
     const char* e = getenv("MDGAN_WGRAD_TG");
-    const int v = e ? atoi(e) : 2;
+    const int v = e ? atoi(e) : 1;
     return v < 1 ? 1 : (v > 2 ? 2 : v);
   }();
   return tg;

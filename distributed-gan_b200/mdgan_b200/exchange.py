@@ -142,6 +142,14 @@ class PeerExchange(Exchange):
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.F_root = self.F if proc == 0 else hf.get_buffer(0, tuple(self.F.shape), torch.float32)
         self._handles = (hx, hf, hg)
+        # NVSwitch multicast mapping of X (one multimem.st per element instead of one store per peer), when the
+        # platform provides it and MDGAN_PEER_MULTICAST != 0
+        import os
+
+        self.X_mc = None
+        mc_ptr = int(getattr(hx, "multicast_ptr", 0) or 0)
+        if proc == 0 and mc_ptr != 0 and os.environ.get("MDGAN_PEER_MULTICAST", "1") != "0":
+            self.X_mc = _tensor_at(mc_ptr, tuple(self.X.shape), device)
         if proc == 0:
             self.x_addrs = torch.tensor([int(p) for p in hx.buffer_ptrs], dtype=torch.int64).to(device)
             self.sig_addrs = torch.tensor([int(hg.buffer_ptrs[p]) for p in range(1, n_procs)] or [0],
@@ -163,7 +171,10 @@ class PeerExchange(Exchange):
         from . import ops
 
         if self.proc == 0:
-            ops.peer_push(X, self.x_addrs, self.n_procs)
+            if self.X_mc is not None:
+                ops.peer_push_multicast(X, self.X_mc)
+            else:
+                ops.peer_push(X, self.x_addrs, self.n_procs)
             if self.n_sig:
                 ops.peer_signal(self.sig_addrs, self.n_sig, self.epoch, advance=False)
         else:
@@ -182,6 +193,17 @@ class PeerExchange(Exchange):
         """Raise if a flag wait timed out (call at a point that synchronises anyway)."""
         if int(self.err.item()) != 0:
             raise RuntimeError("peer exchange: a flag did not arrive within the time-out (a peer process died?)")
+
+
+class _RawCuda:
+    """An fp32 device buffer at a raw address (not owned) for torch.as_tensor: the multicast mapping has no tensor."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _tensor_at(ptr: int, shape, device: torch.device) -> torch.Tensor:
+    return torch.as_tensor(_RawCuda(ptr, shape), device=device)
 
 
 def make_exchange(proc: int, n_procs: int, n_workers: int, device: torch.device, k: int, b: int, image_shape) -> Exchange:

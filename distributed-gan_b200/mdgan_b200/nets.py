@@ -42,7 +42,7 @@ def _conv_bn_act(src, wpacked, mode, c_out, z, a, grid, src_hw, bias, prec, bn_p
     """conv_gemm -> train-mode BatchNorm -> activation.  With fused statistics: GEMM (+ column sums in its epilogue) ->
     bn_finalize -> bn_apply; otherwise GEMM -> bn_forward (statistics pass + apply)."""
     n_cols = c_out if n_cols is None else n_cols
-    plan = ops.conv_stats_plan(grid, mode, G, prec) if (_FUSED_STATS and bn_part is not None) else None
+    plan = ops.conv_stats_plan(grid, mode, G, prec, n_cols) if (_FUSED_STATS and bn_part is not None) else None
     nbt = B[bnp.num_batches_tracked] if bnp.num_batches_tracked else None
     if plan is not None and _stats_floats(plan, ops.n_pad_for(n_cols)) <= bn_part.numel():
         ops.conv_gemm(src, wpacked, mode, n_cols, z, grid, src_hw, bias=bias, precision=prec, bn_partial=bn_part)
@@ -57,6 +57,17 @@ def _conv_bn_act(src, wpacked, mode, c_out, z, a, grid, src_hw, bias, prec, bn_p
 
 def _pad(n: int, m: int) -> int:
     return (n + m - 1) // m * m
+
+
+def _bn_backward(fused_plan, bn_part, n_pad, da, z, stats, dz, dgamma, dbeta, sums, bn_ws, bn_cnt, G, Pg, Cc, act, slope,
+                 round_tf32):
+    """BatchNorm(+activation) backward.  fused_plan is not None: `da` already holds dy = da * act'(.) and bn_part the
+    partial sums, both written by the data-gradient GEMM that produced it (ops.conv_gemm bnb=...)."""
+    if fused_plan is not None:
+        ops.bn_bwd_finalize(bn_part, fused_plan, n_pad, sums, dgamma, dbeta, G, Cc)
+        ops.bn_bwd_apply_dy(da, z, stats, sums, dz, G, Pg, Cc, round_tf32=round_tf32)
+    else:
+        ops.bn_backward(da, z, stats, dz, dgamma, dbeta, sums, bn_ws, bn_cnt, G, Pg, Cc, act, slope, round_tf32=round_tf32)
 
 
 class FlatState:
@@ -217,6 +228,10 @@ class DiscNet:
                     plan = ops.conv_stats_plan((G * batch_size, ly.h_out, ly.h_out), ops.MODE_DOWN, G, self.prec)
                     if plan is not None:
                         part = max(part, _stats_floats(plan, ops.n_pad_for(ly.c_out)))
+                    if l >= 2:  # the data-gradient GEMM of layer l reduces the BatchNorm-backward sums of layer l - 1
+                        plan = ops.conv_stats_plan((G * batch_size, ly.h_out, ly.h_out), ops.MODE_UP, G, self.prec, ly.c_in)
+                        if plan is not None:
+                            part = max(part, _stats_floats(plan, ops.n_pad_for(ly.c_in)))
         self.bn_part = torch.empty(part, **f) if part else None
         head = L[-1]
         self.w_head = torch.empty(head.k * head.k * head.c_in, **f)
@@ -280,12 +295,14 @@ class DiscNet:
         head = L[-1]
         ops.head_backward(self.a[-1][:n], self.w_head, self.dlogit, self.da[-1][:n],
                           Gd[head.weight] if train else None, n, head.k * head.k, head.c_in)
+        fused = None   # plan of the fused BatchNorm-backward reduction of the NEXT layer down, if its producer did it
         for l in range(len(L) - 2, 0, -1):
             ly = L[l]
             Ho, bn = ly.h_out, ly.bn
-            ops.bn_backward(self.da[l][:n], self.z[l][:n], self.stats[l], self.dz[l][:n],
-                            Gd[bn.weight] if train else None, Gd[bn.bias] if train else None, self.sums[l], self.bn_ws,
-                            self.bn_cnt, G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd)
+            _bn_backward(fused, self.bn_part, ops.n_pad_for(ly.c_out), self.da[l][:n], self.z[l][:n], self.stats[l],
+                         self.dz[l][:n], Gd[bn.weight] if train else None, Gd[bn.bias] if train else None, self.sums[l],
+                         self.bn_ws, self.bn_cnt, G, b * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, self.rnd)
+            fused = None
             if train:  # weight gradient on the side stream, next to the data gradient below
                 with ops.side_branch():
                     splits = ops.wgrad_splits(n, Ho, Ho, ly.c_out, ly.c_in, ops.MODE_DOWN)
@@ -297,8 +314,17 @@ class DiscNet:
                               precision=self.prec, gate=self.a[0][:n], gate_act=ops.ACT_LRELU, gate_slope=L[0].slope,
                               round_tf32=(self.rnd and not train))
             else:
-                ops.conv_gemm(self.dz[l][:n], self.wq[l], ops.MODE_UP, ly.c_in, self.da[l - 1][:n], (n, Ho, Ho), (Ho, Ho),
-                              precision=self.prec)
+                prev = L[l - 1]
+                plan = ops.conv_stats_plan((n, Ho, Ho), ops.MODE_UP, G, self.prec, ly.c_in) \
+                    if (_FUSED_STATS and self.bn_part is not None and not self.rnd and ly.c_in % 16 == 0) else None
+                if plan is not None and _stats_floats(plan, ops.n_pad_for(ly.c_in)) <= self.bn_part.numel():
+                    ops.conv_gemm(self.dz[l][:n], self.wq[l], ops.MODE_UP, ly.c_in, self.da[l - 1][:n], (n, Ho, Ho), (Ho, Ho),
+                                  precision=self.prec, bn_partial=self.bn_part,
+                                  bnb=(self.z[l - 1][:n], self.stats[l - 1], _ACT_CODE[prev.act], prev.slope, G))
+                    fused = plan
+                else:
+                    ops.conv_gemm(self.dz[l][:n], self.wq[l], ops.MODE_UP, ly.c_in, self.da[l - 1][:n], (n, Ho, Ho),
+                                  (Ho, Ho), precision=self.prec)
         l0 = L[0]
         if train:
             ops.thin_wgrad(self.dz[0][:n], img[:n], self.partial[0], Gd[l0.weight])
@@ -365,9 +391,12 @@ class GenNet:
         if plan is not None:
             part = _stats_floats(plan, ops.n_pad_for(self.kk * l0.c_out))
         for ly in L[1:-1]:
-            plan = ops.conv_stats_plan((n, ly.h_in, ly.h_in), ops.MODE_UP, 1, self.prec)
+            plan = ops.conv_stats_plan((n, ly.h_in, ly.h_in), ops.MODE_UP, 1, self.prec, ly.c_out)
             if plan is not None:
                 part = max(part, _stats_floats(plan, ops.n_pad_for(ly.c_out)))
+            plan = ops.conv_stats_plan((n, ly.h_in, ly.h_in), ops.MODE_DOWN, 1, self.prec)  # data gradient: BN bwd of l - 1
+            if plan is not None:
+                part = max(part, _stats_floats(plan, ops.n_pad_for(ly.c_in)))
         self.bn_part = torch.empty(part, **f) if part else None
         self.wp_dense = torch.empty(ops.packed_shape(ops.MODE_DENSE, l0.c_out, z_dim, self.kk, self.prec), **f)
         sp0 = ops.wgrad_splits(n, 1, 1, self.zc, self.kk * l0.c_out, ops.MODE_DENSE)
@@ -439,11 +468,14 @@ class GenNet:
         with ops.side_branch():  # weight gradients run next to the data-gradient chain (ops.side_branch)
             ops.thin_wgrad(self.a[-1], self.dXt, self.partial[-1], Gd[last.weight])
         ops.thin_down(self.dXt, P[last.weight], self.da[-1], act=ops.ACT_NONE)
+        fused = None
         for l in range(len(L) - 2, -1, -1):
             ly, bn = L[l], L[l].bn
             Ho = ly.h_out
-            ops.bn_backward(self.da[l], self.z[l], self.stats[l], self.dz[l], Gd[bn.weight], Gd[bn.bias], self.sums[l],
-                            self.bn_ws, self.bn_cnt, 1, n * Ho * Ho, ly.c_out, _ACT_CODE[ly.act], ly.slope, round_tf32=self.rnd)
+            _bn_backward(fused, self.bn_part, ops.n_pad_for(ly.c_out), self.da[l], self.z[l], self.stats[l], self.dz[l],
+                         Gd[bn.weight], Gd[bn.bias], self.sums[l], self.bn_ws, self.bn_cnt, 1, n * Ho * Ho, ly.c_out,
+                         _ACT_CODE[ly.act], ly.slope, self.rnd)
+            fused = None
             if l >= 1:
                 hi = ly.h_in
                 with ops.side_branch():
@@ -451,8 +483,17 @@ class GenNet:
                     ops.wgrad_gemm(self.a[l - 1], self.dz[l], self.partial[l], (n, hi, hi), ops.MODE_DOWN, splits,
                                    precision=self.prec)
                     ops.wgrad_unpack(self.partial[l], Gd[ly.weight], ops.MODE_DOWN, splits, ly.c_in, ly.c_in, ly.c_out)
-                ops.conv_gemm(self.dz[l], self.wp_dg[l], ops.MODE_DOWN, ly.c_in, self.da[l - 1], (n, hi, hi), (Ho, Ho),
-                              precision=self.prec)
+                prev = L[l - 1]
+                plan = ops.conv_stats_plan((n, hi, hi), ops.MODE_DOWN, 1, self.prec) \
+                    if (_FUSED_STATS and self.bn_part is not None and not self.rnd and ly.c_in % 16 == 0) else None
+                if plan is not None and _stats_floats(plan, ops.n_pad_for(ly.c_in)) <= self.bn_part.numel():
+                    ops.conv_gemm(self.dz[l], self.wp_dg[l], ops.MODE_DOWN, ly.c_in, self.da[l - 1], (n, hi, hi), (Ho, Ho),
+                                  precision=self.prec, bn_partial=self.bn_part,
+                                  bnb=(self.z[l - 1], self.stats[l - 1], _ACT_CODE[prev.act], prev.slope, 1))
+                    fused = plan
+                else:
+                    ops.conv_gemm(self.dz[l], self.wp_dg[l], ops.MODE_DOWN, ly.c_in, self.da[l - 1], (n, hi, hi), (Ho, Ho),
+                                  precision=self.prec)
             else:
                 c2 = self.kk * ly.c_out
                 splits = ops.wgrad_splits(n, 1, 1, self.zc, c2, ops.MODE_DENSE)

@@ -226,12 +226,16 @@ def conv_gemm(src: torch.Tensor, wpacked: torch.Tensor, mode: int, N: int, out: 
               grid: Tuple[int, int, int], src_hw: Tuple[int, int], bias: Optional[torch.Tensor] = None,
               out_nchw: bool = False, act_tanh: bool = False, round_tf32: bool = False, accumulate: bool = False,
               precision: int = TF32, force_bn: int = 0, gate: Optional[torch.Tensor] = None, gate_act: int = ACT_NONE,
-              gate_slope: float = 0.0, bn_partial: Optional[torch.Tensor] = None) -> torch.Tensor:
+              gate_slope: float = 0.0, bn_partial: Optional[torch.Tensor] = None, bnb=None) -> torch.Tensor:
     """grid = (n_img, Hg, Wg): the low-resolution row grid; src is NHWC [n_img, Hs, Ws, C].  With precision TF32X3
     `wpacked` must hold the hi and lo matrices (pack_*(..., precision=TF32X3)).  gate (NHWC, shaped like out): the
     result is multiplied by act'(gate) -- the (Leaky)ReLU backward fused into the data gradient that feeds it.
     bn_partial ([phases * row tiles, 2, N_pad], see conv_stats_shape): the GEMM epilogue also reduces the BatchNorm
-    statistics of its output; finish with bn_finalize + bn_apply instead of bn_forward."""
+    statistics of its output; finish with bn_finalize + bn_apply instead of bn_forward.
+    bnb = (z, stats, act, slope, groups) with bn_partial (data-gradient GEMMs): `out` is the gradient of the output of
+    BatchNorm(z)+act; the epilogue stores dy = da * act'(.) and reduces the BatchNorm-backward sums; finish with
+    bn_bwd_finalize + bn_bwd_apply_dy instead of bn_backward."""
+    bz, bst, bact, bslope, bgroups = bnb if bnb is not None else (None, None, 0, 0.0, 1)
     n_img, Hg, Wg = grid
     Hs, Ws = src_hw
     Cc = src.shape[-1]
@@ -244,7 +248,7 @@ def conv_gemm(src: torch.Tensor, wpacked: torch.Tensor, mode: int, N: int, out: 
          lambda: _K.conv_gemm(src, wpacked, out, bias, n_img, Hg, Wg, Hs, Ws, Cc,
                                              mode, N, N_pad, int(out_nchw), int(act_tanh), int(round_tf32),
                                              int(accumulate), precision, force_bn, gate, gate_act,
-                                             float(gate_slope), bn_partial))
+                                             float(gate_slope), bn_partial, bz, bst, bact, float(bslope), bgroups))
     return out
 
 
@@ -253,16 +257,17 @@ def conv_rows_per_tile(Hg: int, Wg: int, precision: int) -> int:
     return _lib.load().mdgan_conv_rows_per_tile(Hg, Wg, precision)
 
 
-def conv_stats_plan(grid: Tuple[int, int, int], mode: int, groups: int, precision: int):
-    """(row_tiles, tiles_per_group, phases) of the fused statistics of conv_gemm over `grid` = (n_img, Hg, Wg) holding
-    `groups` equally sized BatchNorm passes, or None when a CTA's rows would straddle two passes / the mode has no
+def conv_stats_plan(grid: Tuple[int, int, int], mode: int, groups: int, precision: int, n_cols: int = 0):
+    """(row_tiles, tiles_per_group, phases) of the fused statistics of conv_gemm over `grid` = (n_img, Hg, Wg) with
+    n_cols output channels holding `groups` equally sized BatchNorm passes, or None when a CTA's rows would straddle two passes / the mode has no
     fused statistics (callers then use bn_forward)."""
     n_img, Hg, Wg = grid
     rpt = conv_rows_per_tile(Hg, Wg, precision)
     M = n_img * Hg * Wg
     if rpt <= 0 or M % groups != 0 or (M // groups) % rpt != 0:
         return None
-    return M // rpt, M // groups // rpt, 4 if mode == MODE_UP else 1
+    phases = _lib.load().mdgan_conv_stat_phases(mode, n_pad_for(n_cols) if n_cols else 0, Hg, Wg, precision)
+    return M // rpt, M // groups // rpt, phases
 
 
 def wgrad_splits(n_img: int, Hl: int, Wl: int, C1: int, C2: int, mode: int) -> int:
@@ -372,6 +377,18 @@ def bn_backward(da, x, stats, dx, dgamma, dbeta, sums, workspace, counters, G, P
     return dx
 
 
+def bn_bwd_finalize(partial, plan, col_stride, sums, dgamma, dbeta, G, Cc):
+    row_tiles, tpg, phases = plan
+    _run("bn_backward", 1, 0, 4.0 * 2 * phases * row_tiles * col_stride,
+         lambda: _K.bn_bwd_finalize(partial, phases, row_tiles, tpg, col_stride, sums, dgamma, dbeta, G, Cc))
+
+
+def bn_bwd_apply_dy(dy, x, stats, sums, dx, G, Pg, Cc, round_tf32=False):
+    _run("bn_backward", 1, 0, 4.0 * 3 * G * Pg * Cc,
+         lambda: _K.bn_bwd_apply_dy(dy, x, stats, sums, dx, G, Pg, Cc, int(round_tf32)))
+    return dx
+
+
 def act_backward(da, a, dz, act, slope, round_tf32=False):
     _run("act_backward", 1, 0, 4.0 * 3 * a.numel(),
          lambda: _K.act_backward(da, a, dz, a.numel(), act, slope, int(round_tf32)))
@@ -411,6 +428,12 @@ def peer_wait(flags: torch.Tensor, n: int, epoch: torch.Tensor, advance: bool, e
 def peer_push(src: torch.Tensor, dst_addrs: torch.Tensor, n_dst: int):
     _run("peer_push", 1, 0, 4.0 * src.numel() * (1 + n_dst),
          lambda: _K.peer_push(src, dst_addrs, n_dst, src.numel()))
+
+
+def peer_push_multicast(src: torch.Tensor, mc_dst: torch.Tensor):
+    """mc_dst: a tensor view of the NVSwitch multicast address of the symmetric buffer (exchange.PeerExchange)."""
+    _run("peer_push", 1, 0, 4.0 * src.numel() * 2,
+         lambda: _K.peer_push_multicast(src, mc_dst, src.numel()))
 
 
 # ----------------------------------------------------------------------------- head / loss / optimiser

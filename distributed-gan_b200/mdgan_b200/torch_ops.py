@@ -23,7 +23,8 @@ NAMESPACE = "mdgan_b200"
 SPECS: Dict[str, str] = {
     "conv_gemm": "T src, T wpacked, T! dst, T? bias, int n_img, int Hg, int Wg, int Hs, int Ws, int C, int mode, int N, "
                  "int N_pad, int out_nchw, int act, int round_tf32, int accumulate, int precision, int force_bn, "
-                 "T? gate, int gate_act, float gate_slope, T?! bn_partial",
+                 "T? gate, int gate_act, float gate_slope, T?! bn_partial, T? bnb_z, T? bnb_stats, int bnb_act, "
+                 "float bnb_slope, int bnb_groups",
     "wgrad_gemm": "T lo, T hi, T! partial, int n_img, int Hl, int Wl, int C1, int C2, int mode, int splits, int precision",
     "pack_weights": "T W, T! out, int mode, int N, int C, int N_pad, int C_pad, int KK, int split",
     "wgrad_unpack": "T partial, T! grad, int mode, int splits, int C1, int C1p, int C2, int N, int KK",
@@ -34,6 +35,9 @@ SPECS: Dict[str, str] = {
     "bn_finalize": "T partial, int phases, int row_tiles, int tiles_per_group, int col_stride, int fold, T gamma, T beta, "
                    "T?! running_mean, T?! running_var, T?! nbt, T! stats, int G, int Pg, int C, float eps, float momentum",
     "bn_apply": "T x, T stats, T! out, int G, int Pg, int C, int act, float slope, int round_tf32",
+    "bn_bwd_finalize": "T partial, int phases, int row_tiles, int tiles_per_group, int col_stride, T! sums, T?! dgamma, "
+                       "T?! dbeta, int G, int C",
+    "bn_bwd_apply_dy": "T dy, T x, T stats, T sums, T! dx, int G, int Pg, int C, int round_tf32",
     "bn_backward": "T da, T x, T stats, T! dx, T?! dgamma, T?! dbeta, T! sums, T! workspace, T! counters, int G, int Pg, "
                    "int C, int act, float slope, int round_tf32",
     "act_backward": "T da, T a, T! dz, int n, int act, float slope, int round_tf32",
@@ -47,6 +51,7 @@ SPECS: Dict[str, str] = {
     "peer_signal": "T! flag_addrs, int n, T! epoch, int advance",    # writes to the peer-mapped addresses it holds
     "peer_wait": "T flags, int n, T! epoch, int advance, T! err, int timeout_ms",
     "peer_push": "T src, T! dst_addrs, int n_dst, int n",
+    "peer_push_multicast": "T src, T! mc_dst, int n",
     "tanh_backward_slices": "T F, T x, T! out, int n_per_slot, int k, int N, float scale",
     "thin_down": "T img, T W, T! out, int n_img, int CI, int Hi, int Wi, int N, int act, float slope, int round_tf32",
     "thin_up": "T src, T W, T! out, int n_img, int H, int Wd, int C, int N, int act_tanh, int accumulate",

@@ -75,14 +75,23 @@ int mdgan_pack_weights_multi(const long long* jobs_dev, int n_jobs, int total_bl
  * BatchNorm statistics of the layer without another pass over its output; mdgan_bn_finalize turns them into
  * mean / invstd / scale / shift + running statistics.  mdgan_conv_rows_per_tile gives the GEMM rows one CTA owns
  * (row tiles = ceil(n_img*Hg*Wg / rows); 0 = fused statistics unavailable in this mode).
+ * bnb_z / bnb_stats (optional, with bn_partial; data-gradient GEMMs): dst is the gradient of a BatchNorm+activation
+ * OUTPUT; with the BatchNorm input bnb_z (NHWC like dst), its statistics bnb_stats ([bnb_groups][4][N] from
+ * mdgan_bn_forward / mdgan_bn_finalize) and the activation (bnb_act, bnb_slope) the epilogue stores
+ * dy = da * act'(z*scale + shift) and bn_partial receives the column sums of dy and dy * xhat -- the reduction pass of
+ * the BatchNorm backward; finish with mdgan_bn_bwd_finalize + mdgan_bn_bwd_apply_dy instead of mdgan_bn_backward.
  * Replaces: nn.Conv2d(k4,s2,p1) forward CIFAR10.py:88,92 / CelebA.py:81,85,88; nn.ConvTranspose2d forward
  * CIFAR10.py:118-130 / CelebA.py:113-131 (+ torch.tanh CIFAR10.py:131 / CelebA.py:140); and their data
  * gradients computed by loss.backward() (actors/worker.py:204,227) and torch.autograd.grad (actors/server.py:286). */
 int mdgan_conv_gemm(const float* src, const float* wpacked, float* dst, const float* bias, int n_img, int Hg, int Wg,
                     int Hs, int Ws, int C, int mode, int N, int N_pad, int out_nchw, int act, int round_tf32,
                     int accumulate, int precision, int force_bn, const float* gate, int gate_act, float gate_slope,
-                    float* bn_partial, void* stream);
+                    float* bn_partial, const float* bnb_z, const float* bnb_stats, int bnb_act, float bnb_slope,
+                    int bnb_groups, void* stream);
 int mdgan_conv_rows_per_tile(int Hg, int Wg, int precision);
+/* phase slices of bn_partial for this problem: 1 (DOWN / DENSE), 4 (UP), 2 (UP with 64 output channels: one CTA
+ * computes both column parities of an output-row parity). */
+int mdgan_conv_stat_phases(int mode, int N_pad, int Hg, int Wg, int precision);
 
 /* ---- weight gradient, tcgen05 (kind::tf32, MN-major operands), split-K over pixels ----------------------------
  * partial[split][tap][C1][C2] = sum_p lo[p][c1] * hi[gather(p, tap)][c2]; mode DOWN = 16 taps of the k4 s2 p1
@@ -143,6 +152,10 @@ int mdgan_bn_apply(const float* x, const float* stats, float* out, int G, int Pg
 int mdgan_bn_backward(const float* da, const float* x, const float* stats, float* dx, float* dgamma, float* dbeta,
                       float* sums, float* workspace, unsigned int* counters, int G, int Pg, int C, int act, float slope,
                       int round_tf32, void* stream);
+int mdgan_bn_bwd_finalize(const float* partial, int phases, int row_tiles, int tiles_per_group, int col_stride,
+                          float* sums, float* dgamma, float* dbeta, int G, int C, void* stream);
+int mdgan_bn_bwd_apply_dy(const float* dy, const float* x, const float* stats, const float* sums, float* dx, int G, int Pg,
+                          int C, int round_tf32, void* stream);
 int mdgan_act_backward(const float* da, const float* a, float* dz, long long n, int act, float slope, int round_tf32,
                        void* stream);
 /* out = s * (1 - x^2) * scale: backward of the generator's tanh on the group-summed feedback, with the
@@ -186,12 +199,15 @@ int mdgan_sum_slices(const float* in, float* out, long long n, int count, long l
  *     died) sets *err = 1 and TRAPS the kernel: the context is lost and later calls fail, rather than the rest of
  *     the iteration running on stale data.
  *   mdgan_peer_push  : dst_j[0..n) = src[0..n) for the n_dst peer-mapped destinations dst_addrs_dev[j] (n % 4 == 0).
+ *   mdgan_peer_push_multicast: the same through the NVSwitch multicast address mc_dst of the symmetric buffer
+ *     (multimem.st: one store leaves the GPU, the switch writes every copy, the local one included).
  *   mdgan_tanh_backward_slices: out[s][j] = scale * (1 - x[s][j]^2) * sum_{w = s, s+k, .. < N} F[w][j], j < n_per_slot:
  *     the feedbacks of the workers sharing generated batch s, summed in ascending worker order, fused with the
  *     generator's tanh backward (F: [N][n_per_slot] slices written by the workers' feedback kernels). */
 int mdgan_peer_signal(const unsigned long long* flag_addrs_dev, int n, int* epoch, int advance, void* stream);
 int mdgan_peer_wait(const int* flags, int n, int* epoch, int advance, int* err, long long timeout_ms, void* stream);
 int mdgan_peer_push(const float* src, const unsigned long long* dst_addrs_dev, int n_dst, long long n, void* stream);
+int mdgan_peer_push_multicast(const float* src, float* mc_dst, long long n, void* stream);
 int mdgan_tanh_backward_slices(const float* F, const float* x, float* out, long long n_per_slot, int k, int N,
                                float scale, void* stream);
 

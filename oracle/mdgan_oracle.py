@@ -206,9 +206,12 @@ class OracleMDGAN:
 
     # ---- one generator iteration (a reference "epoch")
     def step(self, epoch: int, record: bool = True, z: Optional[torch.Tensor] = None,
-             replay_reals: Optional[Sequence[torch.Tensor]] = None, pairs: Optional[torch.Tensor] = None) -> Dict[str, object]:
+             replay_reals: Optional[Sequence[torch.Tensor]] = None, pairs: Optional[torch.Tensor] = None,
+             record_gates: bool = False) -> Dict[str, object]:
         """z / replay_reals / pairs: replay another run's random draws instead of consuming this oracle's RNG streams and
-        data loaders (used by the tests to run the fp64 twin on exactly the reference's inputs)."""
+        data loaders (used by the tests to run the fp64 twin on exactly the reference's inputs).
+        record_gates: also return, per worker, the sign pattern (output > 0, NCHW bool) of every LeakyReLU of the
+        feedback pass (`fb_gates`) -- the tests use it to tell a rounding-tied gate from a numerical error."""
         N, k, b = self.N, self.k, self.b
         out: Dict[str, object] = {}
         if z is None:
@@ -219,6 +222,7 @@ class OracleMDGAN:
         K = torch.chunk(X, k)  # server.py:223
         feedbacks = torch.zeros((N, b, *self.shape), dtype=self.dtype)
         d_losses, g_losses, reals, d_mid = [], [], [], []
+        fb_gates: List[List[torch.Tensor]] = []
         for n in range(N):
             ig, id_ = route(n, k)
             x_g, x_d = K[ig].detach(), K[id_].detach()
@@ -229,7 +233,13 @@ class OracleMDGAN:
                     losses[l] = d_train_step(self.D[n], self.opt_d[n], real, x_d)
                 if record:  # discriminator state after its Adam step(s), before the feedback pass (test hook)
                     d_mid.append({kk: v.detach().clone() for kk, v in self.D[n].state_dict().items()})
-                loss_gen, F_n = d_feedback(self.D[n], x_g)  # worker.py:220-233
+                if record_gates:
+                    gates_n: List[torch.Tensor] = []
+                    with _record_leaky_relu(gates_n):
+                        loss_gen, F_n = d_feedback(self.D[n], x_g)  # worker.py:220-233
+                    fb_gates.append(gates_n)
+                else:
+                    loss_gen, F_n = d_feedback(self.D[n], x_g)  # worker.py:220-233
             feedbacks[n] = F_n
             d_losses.append(losses.mean().item())
             g_losses.append(loss_gen.item())
@@ -255,7 +265,29 @@ class OracleMDGAN:
         out.update(mean_d_loss=d_losses, loss_gen=g_losses, pairs=pairs)
         if record:
             out.update(z=z, X=X.detach(), feedbacks=feedbacks, delta_w=[g.detach() for g in delta_w], real=reals, d_mid=d_mid)
+        if record_gates:
+            out["fb_gates"] = fb_gates
         return out
+
+
+@contextlib.contextmanager
+def _record_leaky_relu(store: List[torch.Tensor]):
+    """While active, every torch.nn.functional.leaky_relu call (nn.LeakyReLU modules included) appends the sign pattern
+    of its output to `store`.  Test hook only: the arithmetic is untouched."""
+    import torch.nn.functional as F
+
+    orig = F.leaky_relu
+
+    def wrapped(input, negative_slope=0.01, inplace=False):
+        out = orig(input, negative_slope, inplace)
+        store.append(out.detach() > 0)
+        return out
+
+    F.leaky_relu = wrapped
+    try:
+        yield
+    finally:
+        F.leaky_relu = orig
 
 
 class OracleStandalone:

@@ -57,7 +57,10 @@ def time_distributed(dataset: str, n_workers: int, batch: int, steps: int, warmu
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID",
               "GROUP_RANK", "LOCAL_WORLD_SIZE", "ROLE_RANK", "ROLE_WORLD_SIZE"):
         env.pop(k, None)                 # bootstrap.py does its own rendezvous (mp.spawn)
-    cmd = [sys.executable, str(src / "bootstrap.py"), "--backend", "gloo", "--world_size", str(procs),
+    # an even world size (odd K, e.g. the single-GPU configuration K = 1) is refused by the reference's CLI guard only
+    # (bootstrap.py:163-164): launch_any_workers.py repeats the launcher's tail without it
+    entry = src / "bootstrap.py" if procs % 2 == 1 else HERE / "launch_any_workers.py"
+    cmd = [sys.executable, str(entry), "--backend", "gloo", "--world_size", str(procs),
            "--dataset", dataset, "--ranks", f"0..{n_workers}", "--epochs", str(epochs), "--local_epochs", "1",
            "--swap_interval", str(swap_interval), "--device", "cpu", "--batch_size", str(batch), "--iid", "1",
            "--seed", str(seed), "--master_addr", "127.0.0.1", "--master_port", str(_free_port()),
@@ -85,6 +88,7 @@ def time_distributed(dataset: str, n_workers: int, batch: int, steps: int, warmu
 
     return {"ms_per_step": 1e3 * sum(dur) / len(dur), "steps": len(dur), "warmup": warmup, "cores": cores,
             "threads_per_process": threads, "processes": procs, "wall_s": wall, "source": str(src),
+            "launcher": entry.name,
             "phases_ms": {n: phase(n) for n in ("generate_data", "send_data", "recv_data", "agg_gradients",
                                                 "calc_gradients")}}
 

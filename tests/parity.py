@@ -29,11 +29,13 @@ import torch
 
 from util import agrees, plugin, relerr
 
-# along-trajectory tolerances (scale-normalised max error unless noted), default tf32x3 precision
+# along-trajectory tolerances (scale-normalised max error unless noted), default tf32x3 precision.  Measured on B200
+# (tools/parity_report.py, gpurun_out r2: 12 configurations up to CelebA K=8 b=64): loss <= 1.2e-6, X <= 3.0e-6,
+# running <= 2.0e-6, feedback of images without a tied gate <= see S; bounds are <= 10x the worst measured value.
 TOL = {
-    "loss": 2e-4,      # relative, per-worker mean_d_loss and loss_gen
-    "X": 1e-3,         # generated batch
-    "S": 1e-3,         # group-summed feedback = grad-output of the generator backward, per image
+    "loss": 1e-5,      # relative, per-worker mean_d_loss and loss_gen
+    "X": 3e-5,         # generated batch
+    "S": 1e-3,         # group-summed feedback = grad-output of the generator backward, per image (north-star bar)
     "moments": 5e-3,   # Adam exp_avg after the step (== gradient parity), rel. L2 over the flat buffer (one tied
                        # gate in the training pass moves it by ~1e-3; gate-free runs measure ~1e-6..3e-5)
     "update": 1e-1,    # rel. L2 of the applied weight update (w_after - w_before).  Adam's first steps are sign-like
@@ -41,12 +43,22 @@ TOL = {
                        # so this only bounds the flipped fraction (measured 1e-4..5e-2); the gradients themselves
                        # are held to "moments", the Adam arithmetic to tests/test_kernels_gpu.py::test_adam
     "abs_w": 2.1,      # max |w_ours - w_ref| in units of lr
-    "running": 1e-3,   # BatchNorm running statistics
+    "running": 2e-5,   # BatchNorm running statistics
 }
-# Feedback (judged on the reference's post-Adam discriminator weights, see run_engine_vs_oracle): a rounding-tied gate
-# in the feedback pass corrupts one image (BatchNorm spreads a little of it over its batch), so at most S_BAD_IMAGES of
-# the k*b images may miss TOL["S"] while the whole tensor stays within S_L2 (rel. L2; clean iterations: 5e-7..4e-5).
-S_BAD_IMAGES = 0.25
+# the un-patched iteration (mode "unpatched") carries the engine's own post-Adam discriminator weights into the feedback
+# pass and the engine's own feedback into the generator backward: sign-like first Adam steps turn gradient elements at
+# rounding level into +-lr weight differences, so its bounds are those of one chaotic step
+UNPATCHED_TOL = {"loss": 1e-3, "X": 3e-5, "S_l2": 5e-2, "moments": 5e-2, "update": 3e-1, "abs_w": 2.1, "running": 1e-3}
+# Feedback (judged on the reference's post-Adam discriminator weights, see run_engine_vs_oracle).  A LeakyReLU
+# pre-activation that is zero to within fp32 rounding lands on either side of its gate depending on summation order; the
+# gradient of THAT image then differs by O(1e-2) between two correct fp32 implementations.  The harness detects these
+# events exactly: it compares the sign pattern of every LeakyReLU output of the engine's feedback pass with the fp32
+# oracle's, element by element.  Images WITHOUT a sign difference must meet TOL["S"] -- all of them (S_BAD_IMAGES = 0);
+# images with one are listed by index in the report (`tied_gate_images`), may not exceed TIED_IMAGES of the batch and
+# must still stay within S_TIED; the whole tensor stays within S_L2 (rel. L2).
+S_BAD_IMAGES = 0.0
+TIED_IMAGES = 0.35
+S_TIED = 1e-1
 S_L2 = 1e-2
 # free-running drift bounds after <= 4 iterations (rel. L2)
 FREE_TOL = {"loss": 5e-2, "X": 5e-2, "weights_l2": 2e-2}
@@ -57,19 +69,23 @@ def l2err(got: torch.Tensor, ref: torch.Tensor) -> float:
     return ((g - r).norm() / r.norm().clamp_min(1e-30)).item()
 
 
-def feedback_parity(S: torch.Tensor, ref32: torch.Tensor, ref64: torch.Tensor):
-    """(fraction of images whose feedback misses TOL["S"] against both references, worst per-image error among the
-    images that pass, rel. L2 of the whole tensor against the closer reference).  S: [k, b, C, H, W]."""
+def feedback_parity(S: torch.Tensor, ref32: torch.Tensor, ref64: torch.Tensor, tied: torch.Tensor):
+    """S: [k, b, C, H, W]; tied: [k, b] bool, images whose feedback pass had a LeakyReLU sign difference against the
+    fp32 oracle.  Returns (fraction of UNTIED images that miss TOL["S"], worst per-image error among the untied images,
+    worst per-image error among the tied images, rel. L2 of the whole tensor against the closer reference)."""
     S = S.detach().double().cpu()
     per_img = []
     for ref in (ref32.double(), ref64.double()):
         scale = ref.abs().amax(dim=(2, 3, 4), keepdim=True).clamp_min(1e-30)  # per image
         per_img.append(((S - ref).abs() / scale).amax(dim=(2, 3, 4)).reshape(-1))
-    e = torch.minimum(per_img[0], per_img[1])
-    good = e <= TOL["S"]
-    bad_frac = 1.0 - good.double().mean().item()
-    worst_good = e[good].max().item() if good.any() else float("inf")
-    return bad_frac, worst_good, min(l2err(S, ref32), l2err(S, ref64))
+    e32, e = per_img[0], torch.minimum(per_img[0], per_img[1])
+    tied = tied.reshape(-1)
+    untied = ~tied
+    # untied images: same gates as the fp32 oracle, so they are held to the fp32 oracle itself
+    bad_frac = (e32[untied] > TOL["S"]).double().mean().item() if untied.any() else 0.0
+    worst_untied = e32[untied].max().item() if untied.any() else 0.0
+    worst_tied = e[tied].max().item() if tied.any() else 0.0
+    return bad_frac, worst_untied, worst_tied, min(l2err(S, ref32), l2err(S, ref64))
 
 
 def build_actor_modules(mod, n_workers: int, seed: int):
@@ -149,7 +165,9 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
     engine = MDGANEngine(cfg, 0, 1, dev, g, discs, sources)
     scratch = copy.deepcopy(discs[0])  # (constructing a new module would consume the global RNG stream)
     k, b = engine.k, batch_size
-    worst = {c: 0.0 for c in (list(TOL) + ["S_bad_images", "S_l2"] if traj else FREE_TOL)}
+    worst = {c: 0.0 for c in (list(TOL) + ["S_bad_images", "S_l2", "S_tied", "tied_images"] if traj else FREE_TOL)}
+    tol = TOL if mode != "unpatched" else {**TOL, **UNPATCHED_TOL}
+    tied_log: List[str] = []
     failures: List[str] = []
     pairs_ok, nbt_ok = True, True
 
@@ -163,8 +181,9 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
             _copy_oracle(twin, oracle)
             _load_engine(engine, oracle)
         w_before = {"G": _flat(oracle.G.parameters()), **{n: _flat(oracle.D[n].parameters()) for n in range(n_workers)}}
-        ref = oracle.step(e, record=True)
+        ref = oracle.step(e, record=True, record_gates=patched)
         ref64 = twin.step(e, record=True, z=ref["z"], replay_reals=ref["real"], pairs=ref["pairs"]) if twin else None
+        tied = torch.zeros((k, b), dtype=torch.bool)
         engine.generate()
         w_after_adam = {}
         if patched:
@@ -187,6 +206,14 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
                 net.repack()
                 slot = routing.feedback_slot(n, k)
                 engine.g_loss[i].copy_(net.feedback_step(x_g, out=engine.S[slot * b:(slot + 1) * b], accumulate=True))
+                # LeakyReLU sign pattern of THIS feedback pass against the fp32 oracle's, element by element
+                for l, g_ref in enumerate(ref["fb_gates"][n]):
+                    ours = (net.a[l][:b] > 0).permute(0, 3, 1, 2).cpu()
+                    diff = (ours != g_ref).flatten(1)
+                    for img in diff.any(dim=1).nonzero().flatten().tolist():
+                        tied[slot, img] = True
+                        tied_log.append(f"iter {e} worker {n + 1} image {img} layer {l}: "
+                                        f"{int(diff[img].sum())} gate(s), first at flat index {int(diff[img].nonzero()[0])}")
         else:
             engine.train_workers()
             for n in engine.local:  # the feedback pass does not touch the parameters: this is the post-Adam state
@@ -213,12 +240,15 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
                   f"     d_loss {d_l} ref {ref['mean_d_loss']}\n     g_loss {g_l} ref {ref['loss_gen']}\n"
                   f"     per-slot S err {[relerr(S[i], S_ref[i]) for i in range(k)]}", flush=True)
         if traj:
-            check("loss", f"loss@{e}", loss_err <= TOL["loss"], loss_err)
-            check("X", f"X@{e}", agrees(engine.X, ref["X"], ref64["X"], TOL["X"]), relerr(engine.X, ref["X"]))
-            bad_frac, s_err, s_l2 = feedback_parity(S, S_ref, S_ref64)
-            check("S", f"S@{e}", s_err <= TOL["S"], s_err)
-            check("S_bad_images", f"S_bad_images@{e}", bad_frac <= S_BAD_IMAGES, bad_frac)
-            check("S_l2", f"S_l2@{e}", s_l2 <= S_L2, s_l2)
+            check("loss", f"loss@{e}", loss_err <= tol["loss"], loss_err)
+            check("X", f"X@{e}", agrees(engine.X, ref["X"], ref64["X"], tol["X"]), relerr(engine.X, ref["X"]))
+            bad_frac, s_err, s_tied, s_l2 = feedback_parity(S, S_ref, S_ref64, tied)
+            if patched:
+                check("S", f"S@{e}", s_err <= TOL["S"], s_err)
+                check("S_bad_images", f"S_bad_images@{e}", bad_frac <= S_BAD_IMAGES, bad_frac)
+                check("S_tied", f"S_tied@{e}", s_tied <= S_TIED, s_tied)
+                check("tied_images", f"tied_images@{e}", tied.double().mean().item() <= TIED_IMAGES, tied.double().mean().item())
+            check("S_l2", f"S_l2@{e}", s_l2 <= (S_L2 if patched else UNPATCHED_TOL["S_l2"]), s_l2)
             engine.sync_modules()
             # after a swap worker a holds what partner c trained: compare module-for-module (oracle swapped too)
             nets = [("G", engine.gen, g, oracle.G, oracle.opt_g, twin.G, twin.opt_g)]
@@ -229,7 +259,7 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
                 # Adam moments stay with the rank (worker.py:281 copies parameters in place), weights move
                 m_ref, m_ref64 = _adam_flat(opt, theirs, "exp_avg"), _adam_flat(opt64, theirs64, "exp_avg")
                 m_err = min(l2err(net.state.m, m_ref), l2err(net.state.m, m_ref64))
-                check("moments", f"m[{label}]@{e}", m_err <= TOL["moments"], m_err)
+                check("moments", f"m[{label}]@{e}", m_err <= tol["moments"], m_err)
                 if trace:
                     print(f"     moments[{label}]@{e} {m_err:.2e}", flush=True)
                 if label == "G":
@@ -242,9 +272,9 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
                     wa_ref64 = torch.cat([ref64["d_mid"][label][kk].reshape(-1).double() for kk in names])
                     wa = w_after_adam[label]
                 u_err = min(l2err(wa - wb, wa_ref - wb), l2err(wa - wb, wa_ref64 - wb))
-                check("update", f"update[{label}]@{e}", u_err <= TOL["update"], u_err)
+                check("update", f"update[{label}]@{e}", u_err <= tol["update"], u_err)
                 a_err = (wa - wa_ref).abs().max().item() / lr
-                check("abs_w", f"abs_w[{label}]@{e}", a_err <= TOL["abs_w"], a_err)
+                check("abs_w", f"abs_w[{label}]@{e}", a_err <= tol["abs_w"], a_err)
                 sd, rsd, rsd64 = ours.state_dict(), theirs.state_dict(), theirs64.state_dict()
                 assert list(sd.keys()) == list(rsd.keys())
                 for key in sd:
@@ -254,7 +284,7 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
                         # running_mean of a BatchNorm behind a biased conv tracks the chaotic bias
                         continue
                     elif "running" in key:
-                        check("running", f"{label}.{key}@{e}", agrees(sd[key], rsd[key], rsd64[key], TOL["running"]),
+                        check("running", f"{label}.{key}@{e}", agrees(sd[key], rsd[key], rsd64[key], tol["running"]),
                               relerr(sd[key], rsd[key]))
         else:
             check("loss", f"loss@{e}", loss_err <= FREE_TOL["loss"], loss_err)
@@ -271,4 +301,4 @@ def run_engine_vs_oracle(name: str, n_workers: int, batch_size: int, epochs: int
             check("weights_l2", f"weights[{label}]", w_err <= FREE_TOL["weights_l2"], w_err)
     ok = pairs_ok and nbt_ok and not failures
     return {"ok": ok, "mode": mode, "pairs_bit_exact": pairs_ok, "num_batches_tracked_exact": nbt_ok,
-            "failures": failures[:8], **worst}
+            "failures": failures[:8], "tied_gate_images": tied_log[:40], "tied_gate_events": len(tied_log), **worst}

@@ -205,7 +205,7 @@ def test_torch_custom_ops_cover_the_c_abi():
     from mdgan_b200 import _lib, torch_ops
 
     host_only = {"mdgan_abi_version", "mdgan_check_device", "mdgan_wgrad_splits", "mdgan_pack_job_words",
-                 "mdgan_bn_workspace_floats", "mdgan_thin_wgrad_slices", "mdgan_conv_rows_per_tile"}
+                 "mdgan_bn_workspace_floats", "mdgan_thin_wgrad_slices", "mdgan_conv_rows_per_tile", "mdgan_conv_stat_phases"}
     assert {f"mdgan_{n}" for n in torch_ops.SPECS} == set(_lib.SIGNATURES) - host_only
     for name, spec in torch_ops.SPECS.items():
         op = getattr(torch.ops.mdgan_b200, name).default

@@ -34,8 +34,6 @@ def dev():
                                         (4, 128, 256, 8, 0), (3, 256, 512, 8, 0), (64, 64, 128, 32, 0)])
 @pytest.mark.parametrize("prec,tol", PRECISIONS)
 def test_conv_down(ops, dev, n, C, N, H, bn, prec, tol):
-    if prec == 1 and bn > 64:
-        pytest.skip("tf32x3 tiles are at most 64 wide (TMEM holds the split accumulators)")
     torch.manual_seed(1)
     x, W = torch.randn(n, C, H, H), torch.randn(N, C, 4, 4) * 0.05
     bias = torch.randn(N) * 0.1
@@ -305,3 +303,124 @@ def test_tanh_backward_and_sum_slices(ops, dev):
     for slot in range(2):
         ops.sum_slices(fd[slot:], acc[slot], 3, 2 * 35)
     assert relerr(acc[0], f[0] + f[2] + f[4]) < 1e-6 and relerr(acc[1], f[1] + f[3] + f[5]) < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------- fused BatchNorm
+def _bn_ref(z64, gamma, beta, G, slope):
+    """train-mode BatchNorm2d per pass + LeakyReLU(slope) (slope 0 = ReLU) in fp64; z64 NCHW with G passes along dim 0."""
+    outs = []
+    for zc in z64.chunk(G):
+        outs.append(F.leaky_relu(F.batch_norm(zc, None, None, gamma.double(), beta.double(), True, 0.1, 1e-5), slope))
+    return torch.cat(outs)
+
+
+@pytest.mark.parametrize("mode,n,C,N,H,G", [("down", 16, 64, 128, 16, 2), ("down", 8, 128, 256, 8, 1), ("up", 16, 128, 64, 8, 1),
+                                            ("up", 16, 256, 128, 4, 1), ("up", 6, 256, 128, 7, 1), ("up", 8, 128, 64, 14, 1)])
+def test_conv_fused_bn_statistics(ops, dev, mode, n, C, N, H, G):
+    """conv_gemm(bn_partial) + bn_finalize + bn_apply == conv -> train-mode BatchNorm -> activation, including the
+    running statistics, for DOWN (two passes), UP and the paired-parity UP kernel (64 channels)."""
+    torch.manual_seed(21)
+    x = torch.randn(n, C, H, H)
+    gamma, beta = torch.rand(N) + 0.5, torch.randn(N) * 0.1
+    if mode == "down":
+        W = torch.randn(N, C, 4, 4) * 0.05
+        z64 = F.conv2d(x.double(), W.double(), stride=2, padding=1)
+        wp, m, grid, Ho = ops.pack_down(W.to(dev), precision=1), ops.MODE_DOWN, (n, H // 2, H // 2), H // 2
+    else:
+        W = torch.randn(C, N, 4, 4) * 0.05
+        z64 = F.conv_transpose2d(x.double(), W.double(), stride=2, padding=1)
+        wp, m, grid, Ho = ops.pack_up(W.to(dev), precision=1), ops.MODE_UP, (n, H, H), 2 * H
+    ref = _bn_ref(z64, gamma, beta, G, 0.2)
+    plan = ops.conv_stats_plan(grid, m, G, 1, N)
+    assert plan is not None
+    row_tiles, tpg, phases = plan
+    Np = ops.n_pad_for(N)
+    part = torch.full((phases * row_tiles * 2 * Np,), float("nan"), device=dev)
+    z = torch.empty(n, Ho, Ho, N, device=dev)
+    a = torch.empty_like(z)
+    ops.conv_gemm(nhwc(x).to(dev), wp, m, N, z, grid, (H, H), precision=1, bn_partial=part)
+    stats = torch.zeros(G * 4 * N, device=dev)
+    rm, rv = torch.zeros(N, device=dev), torch.ones(N, device=dev)
+    nbt = torch.zeros((), dtype=torch.int64, device=dev)
+    Pg = (n // G) * Ho * Ho
+    ops.bn_finalize(part, plan, Np, 1, gamma.to(dev), beta.to(dev), rm, rv, nbt, stats, G, Pg, N)
+    ops.bn_apply(z, stats, a, G, Pg, N, ops.ACT_LRELU, 0.2)
+    assert relerr(nchw(z), z64) < FP32_TOL
+    assert relerr(nchw(a), ref) < 1e-4
+    assert int(nbt) == G
+    bn = torch.nn.BatchNorm2d(N).double()
+    bn.train()
+    for zc in z64.chunk(G):
+        bn(zc)
+    assert relerr(rm, bn.running_mean) < 1e-4 and relerr(rv, bn.running_var) < 1e-4
+
+
+def test_conv_dense_fused_bn_statistics(ops, dev):
+    """first generator layer: GEMM columns are (position, channel); the finalize folds the k*k positions."""
+    torch.manual_seed(22)
+    n, C, N, k = 128, 100, 256, 4
+    zin, W = torch.randn(n, C, 1, 1), torch.randn(C, N, k, k) * 0.05
+    gamma, beta = torch.rand(N) + 0.5, torch.randn(N) * 0.1
+    z64 = F.conv_transpose2d(zin.double(), W.double())
+    ref = _bn_ref(z64, gamma, beta, 1, 0.0)
+    wp = ops.pack_dense(W.to(dev), precision=1)
+    zp = torch.zeros(n, wp.shape[1], device=dev)
+    ops.pad_rows(zin.view(n, C).to(dev), zp)
+    plan = ops.conv_stats_plan((n, 1, 1), ops.MODE_DENSE, 1, 1, k * k * N)
+    assert plan is not None
+    part = torch.full((plan[2] * plan[0] * 2 * k * k * N,), float("nan"), device=dev)
+    z = torch.empty(n, k, k, N, device=dev)
+    a = torch.empty_like(z)
+    ops.conv_gemm(zp, wp, ops.MODE_DENSE, k * k * N, z, (n, 1, 1), (1, 1), precision=1, bn_partial=part)
+    stats = torch.zeros(4 * N, device=dev)
+    ops.bn_finalize(part, plan, k * k * N, k * k, gamma.to(dev), beta.to(dev), None, None, None, stats, 1, n * k * k, N)
+    ops.bn_apply(z, stats, a, 1, n * k * k, N, ops.ACT_RELU, 0.0)
+    assert relerr(nchw(a), ref) < 1e-4
+
+
+@pytest.mark.parametrize("mode,n,C,N,H,G", [("up", 16, 128, 64, 8, 2), ("up", 8, 256, 128, 4, 1), ("down", 16, 128, 256, 16, 1)])
+def test_conv_fused_bn_backward(ops, dev, mode, n, C, N, H, G):
+    """Data-gradient GEMM with the BatchNorm-backward reduction in its epilogue (bnb) + bn_bwd_finalize +
+    bn_bwd_apply_dy == autograd through  z -> BatchNorm -> LeakyReLU -> [conv whose data gradient the GEMM is]."""
+    torch.manual_seed(23)
+    gamma, beta = torch.rand(N) + 0.5, torch.randn(N) * 0.1
+    g = torch.randn(n, C, H, H)          # gradient arriving at the GEMM's source
+    if mode == "up":    # data gradient of a Conv2d(N -> C): da = conv_transpose(g, W), W [C, N, 4, 4]
+        W = torch.randn(C, N, 4, 4) * 0.05
+        Ho = 2 * H
+        wp, m, grid = ops.pack_up(W.to(dev), precision=1), ops.MODE_UP, (n, H, H)
+        fwd = lambda a_: F.conv2d(a_, W.double(), stride=2, padding=1)
+    else:               # data gradient of a ConvTranspose2d(N -> C): da = conv(g, W), W [N, C, 4, 4]
+        W = torch.randn(N, C, 4, 4) * 0.05
+        Ho = H // 2
+        wp, m, grid = ops.pack_down(W.to(dev), precision=1), ops.MODE_DOWN, (n, Ho, Ho)
+        fwd = lambda a_: F.conv_transpose2d(a_, W.double(), stride=2, padding=1)
+    z = torch.randn(n, N, Ho, Ho)
+    z64 = z.double().requires_grad_(True)
+    gm, bt = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    outs = []
+    for zc in z64.chunk(G):
+        outs.append(F.leaky_relu(F.batch_norm(zc, None, None, gm, bt, True, 0.1, 1e-5), 0.2))
+    fwd(torch.cat(outs)).backward(g.double())
+    # forward statistics on the device (unfused kernels), then the fused backward
+    Pg = (n // G) * Ho * Ho
+    zd = nhwc(z).to(dev)
+    stats = torch.zeros(G * 4 * N, device=dev)
+    ws = torch.empty(ops.bn_workspace_floats(G, Pg, N), device=dev)
+    cnt = ops.bn_counters(dev)
+    ops.bn_forward(zd, torch.empty_like(zd), gamma.to(dev), beta.to(dev), None, None, None, stats, ws, cnt, G, Pg, N,
+                   ops.ACT_LRELU, 0.2)
+    plan = ops.conv_stats_plan(grid, m, G, 1, N)
+    assert plan is not None
+    Np = ops.n_pad_for(N)
+    part = torch.full((plan[2] * plan[0] * 2 * Np,), float("nan"), device=dev)
+    dy = torch.empty(n, Ho, Ho, N, device=dev)
+    ops.conv_gemm(nhwc(g).to(dev), wp, m, N, dy, grid, (H, H), precision=1, bn_partial=part,
+                  bnb=(zd, stats, ops.ACT_LRELU, 0.2, G))
+    sums = torch.zeros(G * 2 * N, device=dev)
+    dgamma, dbeta = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
+    ops.bn_bwd_finalize(part, plan, Np, sums, dgamma, dbeta, G, N)
+    dz = torch.empty_like(dy)
+    ops.bn_bwd_apply_dy(dy, zd, stats, sums, dz, G, Pg, N)
+    assert relerr(nchw(dz), z64.grad) < 1e-4
+    assert relerr(dgamma, gm.grad) < 1e-4 and relerr(dbeta, bt.grad) < 1e-4

@@ -17,7 +17,7 @@ CASES = [  # name, N, b, epochs, swap_interval
 ]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     CASES = CASES[:2]
-for mode in ("trajectory", "unpatched", "free"):
+for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("trajectory", "unpatched", "free")):
     for c in CASES:
         t0 = time.time()
         r = run_engine_vs_oracle(*c, mode=mode)
