@@ -315,7 +315,7 @@ def _bn_ref(z64, gamma, beta, G, slope):
 
 
 @pytest.mark.parametrize("mode,n,C,N,H,G", [("down", 16, 64, 128, 16, 2), ("down", 8, 128, 256, 8, 1), ("up", 16, 128, 64, 8, 1),
-                                            ("up", 16, 256, 128, 4, 1), ("up", 6, 256, 128, 7, 1), ("up", 8, 128, 64, 14, 1)])
+                                            ("up", 16, 256, 128, 4, 1), ("up", 6, 256, 128, 7, 1), ("up", 32, 128, 64, 14, 1)])
 def test_conv_fused_bn_statistics(ops, dev, mode, n, C, N, H, G):
     """conv_gemm(bn_partial) + bn_finalize + bn_apply == conv -> train-mode BatchNorm -> activation, including the
     running statistics, for DOWN (two passes), UP and the paired-parity UP kernel (64 channels)."""
