@@ -371,7 +371,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
     tc_fence_before_sync();
   } else if (warp == 8) {
     // ------------------------------------------------------------------ B producer (TMA)
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane; keeps the role's code warp-uniform for ptxas (see ptx.cuh)
       const int row0 = (p.mode == 1 ? phase * p.N_pad : 0) + n0;
       int s = 0;
       uint32_t par = 0;
@@ -390,7 +390,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvGemmParam
     // (K-slice offset inside the swizzle atom, hi/lo offset, accumulator column) is an immediate of the unrolled
     // body: a tcgen05.mma 128 x BN x 8 costs max(44, BN/2) clk (tools/micro/umma_micro.cu), an issue loop that
     // rebuilds descriptors or takes a modulo per MMA costs more than that.
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane; keeps the role's code warp-uniform for ptxas (see ptx.cuh)
       constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
       const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
       constexpr uint64_t kStageStep = S::kStageBytes >> 4, kBStep = S::kABytes >> 4, kLoStep = S::kHalfBytes >> 4;
@@ -451,15 +451,27 @@ struct ConvTaSmem {
   static constexpr int kRawStages = 4;
   static constexpr int kBBytes = BN * 128;              // one of hi / lo
   static constexpr int kBStageBytes = 2 * kBBytes;      // [B_hi | B_lo]
+  // MDGAN_CONV_DEEP (experiment build, `make VARIANT=deep`): 128-wide tiles with ONE main accumulator (+ the correction
+  // accumulator) so that four TMEM stages of the activation operand and four weight stages fit -- tests whether the
+  // depth of the operand pipeline, rather than bandwidth, paces the K step.
+#ifdef MDGAN_CONV_DEEP
+  static constexpr int kBStages = 4;
+  static constexpr int kAStages = BN > 64 ? 4 : 3;
+#else
   static constexpr int kBStages = BN > 64 ? 3 : 4;
   static constexpr int kAStages = BN > 64 ? 2 : 3;      // TMEM stages of [A_hi (32 columns) | A_lo (32 columns)]
+#endif
   static constexpr int kBOff = kRawStages * kRawBytes;
   static constexpr int kBarOffset = kBOff + kBStages * kBStageBytes;
   static constexpr int kNumBars = 2 * kRawStages + 2 * kBStages + 2 * kAStages + 1;
   static constexpr int kRedOff = kBarOffset + kNumBars * 8 + 16;   // [4][2][BN] floats: fused BatchNorm statistics
   static constexpr int kTotal = kRedOff + 4 * 2 * BN * 4;
   static constexpr int kDynamic = kTotal + 1024;
+#ifdef MDGAN_CONV_DEEP
+  static constexpr int kMain = BN > 64 ? 1 : 4;
+#else
   static constexpr int kMain = BN > 64 ? 2 : 4;
+#endif
   static constexpr int kAccs = kMain + 1;
   static constexpr int kACol0 = kAccs * BN;
   static constexpr uint32_t kTmemCols = 512;
@@ -637,7 +649,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     }
   } else if (TMA_A && warp == 14) {
     // ------------------------------------------------------------------ activation tile producer (TMA, 4-D box)
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane; keeps the role's code warp-uniform for ptxas (see ptx.cuh)
       const int SIa = (p.mode == 0) ? 2 : 1;
       const int n_start = m0 / (p.Hg * p.Wg);
       const int h_start = (m0 - n_start * (p.Hg * p.Wg)) / p.Wg;
@@ -658,7 +670,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     }
   } else if (warp == 12) {
     // ------------------------------------------------------------------ B producer (TMA, hi + lo)
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane; keeps the role's code warp-uniform for ptxas (see ptx.cuh)
       const int row0 = (p.mode == 1 ? phase * p.N_pad : 0) + n0;
       int s = 0;
       uint32_t par = 0;
@@ -691,7 +703,7 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     }
   } else if (warp == 13) {
     // ------------------------------------------------------------------ MMA issuer (A from TMEM, B from shared memory)
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane; keeps the role's code warp-uniform for ptxas (see ptx.cuh)
       constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
       const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem + S::kBOff), 16, 1024);
       constexpr uint64_t kBStageStep = S::kBStageBytes >> 4, kLoStep = S::kBBytes >> 4;

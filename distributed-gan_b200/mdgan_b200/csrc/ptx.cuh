@@ -12,6 +12,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a CONVERGED warp (elect.sync).  Use this -- not `lane == 0` -- to guard single-thread roles that issue
+// tcgen05.mma / TMA: under `if (lane == 0)` ptxas cannot prove that the operands it must place in uniform registers
+// (descriptors, TMEM addresses) are warp-uniform and wraps EVERY UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+// "waterfall" loop (~10 instructions and several register-to-uniform round trips per MMA: the issue loop then takes
+// longer than the MMAs it issues -- round 2, profiles/r02_mma_issue_sass.md); under elect.sync the twelve MMAs of a K
+// step are issued back to back.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const WgradPar
     tc_fence_before_sync();
   } else {
     // ---------------------------------------------------------------- MMA issuer (lean loop, see conv_gemm.cu)
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane; keeps the role's code warp-uniform for ptxas (see ptx.cuh)
       constexpr uint32_t idesc = make_idesc_tf32(kWM, BN, 1, 1);
       const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem), p.lbo_a, p.sbo_a, 1);
       constexpr uint64_t kStageStep = S::kStageBytes >> 4, kBStep = S::kABytes >> 4, kLoStep = S::kHalfBytes >> 4;
@@ -477,7 +477,7 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
     tc_fence_before_sync();
   } else if (warp == kTmaWarp) {
     // ---------------------------------------------------------------- Lo TMA issuer: 4 boxes of 32 pixels x 32 channels
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane; keeps the role's code warp-uniform for ptxas (see ptx.cuh)
       int s = 0;
       uint32_t par = 0;
       for (int it = 0; it < ksteps; ++it) {
@@ -492,7 +492,7 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
     }
   } else {
     // ---------------------------------------------------------------- MMA issuer: A from TMEM, B (MN-major) from smem
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane; keeps the role's code warp-uniform for ptxas (see ptx.cuh)
       constexpr uint32_t idesc = make_idesc_tf32(kWM, BN, 0, 1);
       const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem), p.lbo_b, p.sbo_b, 1);
       constexpr uint64_t kStageStep = S::kStageBytes >> 4, kLoStep = S::kBBytes >> 4;
