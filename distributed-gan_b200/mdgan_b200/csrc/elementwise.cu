@@ -329,11 +329,21 @@ bn_finalize_kernel(const float* __restrict__ partial, int phases, int row_tiles,
   const int per_group = phases * tiles_per_group * fold;
   for (int g = 0; g < G; ++g) {
     double sum = 0.0, sq = 0.0;
-    for (int i = lane; i < per_group; i += 32) {
+    auto slice = [&](int i) {
       const int f = i % fold, r = i / fold;
       const int t = r % tiles_per_group, ph = r / tiles_per_group;
-      const float* sl = partial + (static_cast<long long>(ph) * row_tiles + g * tiles_per_group + t) * 2 * col_stride +
-                        f * C + c;
+      return partial + (static_cast<long long>(ph) * row_tiles + g * tiles_per_group + t) * 2 * col_stride + f * C + c;
+    };
+    int i = lane;
+    for (; i + 96 < per_group; i += 128) {   // four slices per lane in flight (the loads are independent, the adds ordered)
+      const float* s0 = slice(i); const float* s1 = slice(i + 32); const float* s2 = slice(i + 64); const float* s3 = slice(i + 96);
+      const float a0 = __ldcg(s0), b0 = __ldcg(s0 + col_stride), a1 = __ldcg(s1), b1 = __ldcg(s1 + col_stride);
+      const float a2 = __ldcg(s2), b2 = __ldcg(s2 + col_stride), a3 = __ldcg(s3), b3 = __ldcg(s3 + col_stride);
+      sum += a0; sum += a1; sum += a2; sum += a3;
+      sq += b0; sq += b1; sq += b2; sq += b3;
+    }
+    for (; i < per_group; i += 32) {
+      const float* sl = slice(i);
       sum += __ldcg(sl);
       sq += __ldcg(sl + col_stride);
     }
@@ -498,9 +508,20 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int phases, int row_ti
   double tg = 0.0, tb = 0.0;
   for (int g = 0; g < G; ++g) {
     double sum = 0.0, sq = 0.0;
-    for (int i = lane; i < per_group; i += 32) {
+    auto slice = [&](int i) {
       const int t = i % tiles_per_group, ph = i / tiles_per_group;
-      const float* sl = partial + (static_cast<long long>(ph) * row_tiles + g * tiles_per_group + t) * 2 * col_stride + c;
+      return partial + (static_cast<long long>(ph) * row_tiles + g * tiles_per_group + t) * 2 * col_stride + c;
+    };
+    int i = lane;
+    for (; i + 96 < per_group; i += 128) {   // four slices per lane in flight
+      const float* s0 = slice(i); const float* s1 = slice(i + 32); const float* s2 = slice(i + 64); const float* s3 = slice(i + 96);
+      const float a0 = __ldcg(s0), b0 = __ldcg(s0 + col_stride), a1 = __ldcg(s1), b1 = __ldcg(s1 + col_stride);
+      const float a2 = __ldcg(s2), b2 = __ldcg(s2 + col_stride), a3 = __ldcg(s3), b3 = __ldcg(s3 + col_stride);
+      sum += a0; sum += a1; sum += a2; sum += a3;
+      sq += b0; sq += b1; sq += b2; sq += b3;
+    }
+    for (; i < per_group; i += 32) {
+      const float* sl = slice(i);
       sum += __ldcg(sl);
       sq += __ldcg(sl + col_stride);
     }

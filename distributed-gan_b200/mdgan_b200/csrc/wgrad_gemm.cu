@@ -334,7 +334,7 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
 
   pdl_trigger();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S::kStages; ++s) { mbar_init(&b_full[s], kWProducerWarps); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < S::kStages; ++s) { mbar_init(&b_full[s], kWProducerWarps / 2); mbar_init(&b_empty[s], 1); }  // one group's four warps
     for (int s = 0; s < S::kRawStages; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
     for (int s = 0; s < S::kAStages; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
     mbar_init(tmem_full_bar, 1);
@@ -383,10 +383,17 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
     }
   } else if (warp < kTmaWarp) {
     // ---------------------------------------------------------------- Hi producers (shared memory), then epilogue
-    const int tid = threadIdx.x - kProd0 * 32;
+    // Two groups of four warps take alternate K steps.  A group's step: wait for the stage -> split + store the tile it
+    // holds in registers -> fence.proxy.async -> arrive -> ONLY THEN issue the global loads of its next step.  The order
+    // matters: fence.proxy.async is a MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS, i.e. it waits for EVERY outstanding
+    // memory operation of the thread; with loads prefetched several K steps ahead (round 1) each step stalled for a
+    // full L2 round trip (~1.2 us per K step measured, 3x the MMA time).  Here no load is in flight at the fence, and a
+    // group's load latency is covered by the other group's step.
+    const int grp = (warp - kProd0) >> 2;                 // 0 / 1
+    const int tid = threadIdx.x - (kProd0 + 4 * grp) * 32;  // 0..127 inside the group
     const uint32_t smem0 = smem_u32(smem);
     constexpr int kBChunksPerRow = BN / 4;
-    constexpr int kBRowsPerPass = 256 / kBChunksPerRow;
+    constexpr int kBRowsPerPass = 128 / kBChunksPerRow;
     constexpr int kBPasses = kWK / kBRowsPerPass;
     const int b_cidx = tid % kBChunksPerRow;
     const int b_row0 = tid / kBChunksPerRow;
@@ -397,11 +404,12 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
       const int r = b_row0 + kBRowsPerPass * i;
       b_soff[i] = (b_cidx >> 3) * (kWK * 128) + r * 128 + swz32(b_cidx & 7, r);
     }
-    int pbase_l = pix0;
-    auto issue_loads = [&](float4(&bbuf)[kBPasses]) {
+    float4 bbuf[kBPasses];
+    auto issue_loads = [&](int it) {
+      const int pbase = pix0 + it * kWK;
 #pragma unroll
       for (int i = 0; i < kBPasses; ++i) {
-        const int pix = pbase_l + b_row0 + kBRowsPerPass * i;
+        const int pix = pbase + b_row0 + kBRowsPerPass * i;
         bool ok = pix < pix1;
         size_t off = 0;
         if (ok) {
@@ -415,31 +423,19 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
         }
         bbuf[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.hi + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      pbase_l += kWK;
     };
-    constexpr int kPf = 4;
-    float4 bbuf[kPf][kBPasses];
+    if (grp < ksteps) issue_loads(grp);
+    for (int it = grp; it < ksteps; it += 2) {
+      const int s = it % S::kStages;
+      const uint32_t par = (it / S::kStages) & 1;
+      mbar_wait(&b_empty[s], par ^ 1);
+      const uint32_t stage = smem0 + s * S::kStageBytes;
 #pragma unroll
-    for (int u = 0; u < kPf; ++u)
-      if (u < ksteps) issue_loads(bbuf[u]);
-    int s = 0;
-    uint32_t par = 0;
-    for (int it0 = 0; it0 < ksteps; it0 += kPf) {
-#pragma unroll
-      for (int u = 0; u < kPf; ++u) {
-        const int it = it0 + u;
-        if (it < ksteps) {
-          mbar_wait(&b_empty[s], par ^ 1);
-          const uint32_t stage = smem0 + s * S::kStageBytes;
-#pragma unroll
-          for (int i = 0; i < kBPasses; ++i) store_split<true>(stage + b_soff[i], S::kBBytes, bbuf[u][i]);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&b_full[s]);
-          if (it + kPf < ksteps) issue_loads(bbuf[u]);
-          if (++s == S::kStages) { s = 0; par ^= 1; }
-        }
-      }
+      for (int i = 0; i < kBPasses; ++i) store_split<true>(stage + b_soff[i], S::kBBytes, bbuf[i]);
+      fence_proxy_async_smem();   // no global load of this thread is in flight here (see above)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_full[s]);
+      if (it + 2 < ksteps) issue_loads(it + 2);
     }
     // epilogue: TMEM -> partial[split][tap]
     if (ksteps > 0) {
