@@ -38,6 +38,10 @@ constexpr int kWK = 32;  // pixels per stage
 constexpr int kWProducerWarps = 8;
 constexpr int kWThreads = (kWProducerWarps + 1) * 32;
 constexpr int kWPrefetch = 3;  // K steps of operand loads kept in flight in registers per producer thread
+#ifndef MDGAN_WGRAD_HI_GROUPS
+#define MDGAN_WGRAD_HI_GROUPS 4
+#endif
+constexpr int kHiGroups = MDGAN_WGRAD_HI_GROUPS;  // producer-warp groups of the TMEM-operand kernel (see its Hi producers)
 
 // Byte offset of 16-byte chunk `c16` (0..7) of pixel row `r` inside its 128-byte row under SWIZZLE_128B_BASE32B:
 // the 32-byte chunk index is XORed with (row & 3).
@@ -334,7 +338,7 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
 
   pdl_trigger();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S::kStages; ++s) { mbar_init(&b_full[s], kWProducerWarps / 2); mbar_init(&b_empty[s], 1); }  // one group's four warps
+    for (int s = 0; s < S::kStages; ++s) { mbar_init(&b_full[s], kWProducerWarps / kHiGroups); mbar_init(&b_empty[s], 1); }  // one group's warps
     for (int s = 0; s < S::kRawStages; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
     for (int s = 0; s < S::kAStages; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
     mbar_init(tmem_full_bar, 1);
@@ -383,27 +387,27 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
     }
   } else if (warp < kTmaWarp) {
     // ---------------------------------------------------------------- Hi producers (shared memory), then epilogue
-    // Two groups of four warps take alternate K steps.  A group's step: wait for the stage -> split + store the tile it
-    // holds in registers -> fence.proxy.async -> arrive -> ONLY THEN issue the global loads of its next step.  The order
-    // matters: fence.proxy.async is a MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS, i.e. it waits for EVERY outstanding
-    // memory operation of the thread; with loads prefetched several K steps ahead (round 1) each step stalled for a
-    // full L2 round trip (~1.2 us per K step measured, 3x the MMA time).  Here no load is in flight at the fence, and a
-    // group's load latency is covered by the other group's step.
-    const int grp = (warp - kProd0) >> 2;                 // 0 / 1
-    const int tid = threadIdx.x - (kProd0 + 4 * grp) * 32;  // 0..127 inside the group
+    // kHiGroups groups of warps take K steps round-robin.  A group's step: wait for the stage -> split + store the tile
+    // it holds in registers -> fence.proxy.async -> arrive -> ONLY THEN issue the global loads of its next step.  The
+    // order matters: fence.proxy.async is a MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS, i.e. it waits for EVERY
+    // outstanding memory operation of the thread; with loads prefetched several K steps ahead (round 1) each step
+    // stalled for a full L2 round trip (~1.2 us per K step measured, 3x the MMA time).  Here no load is in flight at the
+    // fence, and a group's load latency (~1.3 us under load) is covered by the other groups' steps.
+    constexpr int kGroupWarps = kWProducerWarps / kHiGroups, kGroupThreads = 32 * kGroupWarps;
+    const int grp = (warp - kProd0) / kGroupWarps;
+    const int tid = threadIdx.x - (kProd0 + kGroupWarps * grp) * 32;  // inside the group
     const uint32_t smem0 = smem_u32(smem);
     constexpr int kBChunksPerRow = BN / 4;
-    constexpr int kBRowsPerPass = 128 / kBChunksPerRow;
+    constexpr int kBRowsPerPass = kGroupThreads / kBChunksPerRow;
     constexpr int kBPasses = kWK / kBRowsPerPass;
+    static_assert(kBRowsPerPass >= 1 && kBPasses * kBRowsPerPass == kWK, "Hi tile split over one producer group");
     const int b_cidx = tid % kBChunksPerRow;
     const int b_row0 = tid / kBChunksPerRow;
     const int hw_l = p.Hl * p.Wl;
-    uint32_t b_soff[kBPasses];
-#pragma unroll
-    for (int i = 0; i < kBPasses; ++i) {
+    auto b_soff = [&](int i) {
       const int r = b_row0 + kBRowsPerPass * i;
-      b_soff[i] = (b_cidx >> 3) * (kWK * 128) + r * 128 + swz32(b_cidx & 7, r);
-    }
+      return static_cast<uint32_t>((b_cidx >> 3) * (kWK * 128) + r * 128) + swz32(b_cidx & 7, r);
+    };
     float4 bbuf[kBPasses];
     auto issue_loads = [&](int it) {
       const int pbase = pix0 + it * kWK;
@@ -425,17 +429,17 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
       }
     };
     if (grp < ksteps) issue_loads(grp);
-    for (int it = grp; it < ksteps; it += 2) {
+    for (int it = grp; it < ksteps; it += kHiGroups) {
       const int s = it % S::kStages;
       const uint32_t par = (it / S::kStages) & 1;
       mbar_wait(&b_empty[s], par ^ 1);
       const uint32_t stage = smem0 + s * S::kStageBytes;
 #pragma unroll
-      for (int i = 0; i < kBPasses; ++i) store_split<true>(stage + b_soff[i], S::kBBytes, bbuf[i]);
+      for (int i = 0; i < kBPasses; ++i) store_split<true>(stage + b_soff(i), S::kBBytes, bbuf[i]);
       fence_proxy_async_smem();   // no global load of this thread is in flight here (see above)
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_full[s]);
-      if (it + 2 < ksteps) issue_loads(it + 2);
+      if (it + kHiGroups < ksteps) issue_loads(it + kHiGroups);
     }
     // epilogue: TMEM -> partial[split][tap]
     if (ksteps > 0) {
