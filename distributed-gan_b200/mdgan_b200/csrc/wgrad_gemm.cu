@@ -38,8 +38,10 @@ constexpr int kWK = 32;  // pixels per stage
 constexpr int kWProducerWarps = 8;
 constexpr int kWThreads = (kWProducerWarps + 1) * 32;
 constexpr int kWPrefetch = 3;  // K steps of operand loads kept in flight in registers per producer thread
+// 2 groups: 62-74 us per CelebA b=64 layer; 4 groups: 57-66 us, but three of six benchmark processes started right after
+// another GPU process stalled with that build (round 2, gpurun calls 9-11; never with 2 groups) -- not understood, so 2.
 #ifndef MDGAN_WGRAD_HI_GROUPS
-#define MDGAN_WGRAD_HI_GROUPS 4
+#define MDGAN_WGRAD_HI_GROUPS 2
 #endif
 constexpr int kHiGroups = MDGAN_WGRAD_HI_GROUPS;  // producer-warp groups of the TMEM-operand kernel (see its Hi producers)
 

@@ -13,8 +13,14 @@ from util import plugin
 pytestmark = pytest.mark.gpu
 
 
-def test_bootstrap_single_gpu_matches_oracle(tmp_path, monkeypatch):
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_bootstrap_matches_oracle(tmp_path, monkeypatch, gpus):
+    """gpus = 1: server + both workers in one process; gpus = 2 (needs two GPUs): one process per GPU spawned by
+    bootstrap.main exactly like the reference's mp.spawn, peer-memory exchange, phase graphs, CSV spans from events."""
     import bootstrap
+
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
     from datasets.DataPartitioner import SyntheticImages
     from mdgan_b200.node import SERVER_COLUMNS, WORKER_COLUMNS
     from oracle.mdgan_oracle import OracleMDGAN
@@ -25,7 +31,8 @@ def test_bootstrap_single_gpu_matches_oracle(tmp_path, monkeypatch):
     bootstrap.main(["--backend", "nccl", "--world_size", str(N + 1), "--ranks", f"0..{N}", "--dataset", "CIFAR10",
                     "--epochs", str(epochs), "--local_epochs", "1", "--swap_interval", "2", "--device", "cuda",
                     "--batch_size", str(b), "--iid", "1", "--seed", "3", "--beta_1", "0.5", "--generator_lr", "0.0002",
-                    "--discriminator_lr", "0.0002", "--log_interval", "1000", "--gpus", "1", "--synthetic", str(m)])
+                    "--discriminator_lr", "0.0002", "--log_interval", "1000", "--gpus", str(gpus), "--synthetic", str(m),
+                    "--master_addr", "127.0.0.1", "--master_port", "29533"])
     monkeypatch.delenv("MDGAN_SYNTH_M", raising=False)
     mod = plugin("CIFAR10")
     oracle = OracleMDGAN(mod.Generator, mod.Discriminator, SyntheticImages(mod.SHAPE, m), N, b, mod.Z_DIM, mod.SHAPE,
@@ -56,6 +63,10 @@ def test_bootstrap_single_gpu_matches_oracle(tmp_path, monkeypatch):
     srows = list(csv.DictReader(open(tmp_path / "logs" / f"mdgan.{N}.CIFAR10.server.logs.csv")))
     assert list(srows[0].keys()) == SERVER_COLUMNS and len(srows) == epochs
     assert [r["swap"] for r in srows] == ["False", "False", "True", "False", "True"]
+    for r in srows:  # device-event spans: ordered phases of positive length
+        t = [float(r[c]) for c in ("start.epoch_calculation", "end.generate_data", "end.recv_data", "end.agg_gradients",
+                                   "end.epoch_calculation")]
+        assert all(b_ >= a_ for a_, b_ in zip(t, t[1:])) and t[-1] > t[0]
     assert (tmp_path / "saved_images" / "real_images.png").exists()
     assert (tmp_path / "saved_images" / f"generated_epoch_{epochs - 1}.png").exists()
     # the asynchronous snapshot of the last epoch (side-stream copy + writer thread) holds exactly the final state
