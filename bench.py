@@ -410,14 +410,25 @@ def run_ours(args) -> None:
             epoch += 1
         sync_all()
         clocks = sampler.stop() if sampler else None
-        ms = max_over_ranks(sum(s_.elapsed_time(e_) for s_, e_ in ev)) / steps
+        mine = sum(s_.elapsed_time(e_) for s_, e_ in ev) / steps
+        ms = max_over_ranks(mine * steps) / steps
+        per_rank = None
+        if world > 1:   # every rank's own device time per step (rank 0 also runs the generator)
+            try:
+                t = torch.zeros(world, device=dev, dtype=torch.float64)
+                t[rank] = mine
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                per_rank = [round(x, 4) for x in t.tolist()]
+            except Exception:  # noqa: BLE001 -- diagnostics only
+                per_rank = None
         return engine, mod, dataset, shards, {"ms_per_step": ms, "launches_per_step": counter.kernels, "swaps": swaps,
-                                               "clocks": clocks}
+                                               "clocks": clocks, "per_rank_ms": per_rank}
 
     # ---------------------------------------------------------------- device-resident leg (`value`)
     engine, mod, dataset, shards, leg = device_leg(args.dataset, args.swap_interval, args.steps, args.warmup, True)
     shape = tuple(mod.SHAPE)
     ms_per_step, launches_per_step, clocks = leg["ms_per_step"], leg["launches_per_step"], leg["clocks"]
+    push_mode = getattr(engine.exchange, "push_mode", None)
     gen_it_s = 1e3 / ms_per_step
     value = gen_it_s * n_workers
 
@@ -483,6 +494,17 @@ def run_ours(args) -> None:
                                  "frac_of_mode_ceiling": t_fl / (t_ms * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] / (6.0 if x3 else 2.0)),
                                  "share_of_step": t_ms / total_ms}
     step_flops = sum(v["flops"] for v in per_op.values()) / 4
+    # exchange kernels of the instrumented eager iteration on EVERY rank: a flag wait shows how long that rank idled
+    exchange_us = None
+    if world > 1:
+        try:
+            mine_x = {n: round(per_op[n]["ms"] * 1e3 / 4, 2) for n in ("peer_push", "peer_signal", "peer_wait") if n in per_op}
+            mine_x["iteration"] = round(total_ms * 1e3 / 4, 1)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine_x)
+            exchange_us = gathered
+        except Exception:  # noqa: BLE001 -- diagnostics only
+            exchange_us = None
     engine.close()
     exchange_mode = getattr(engine.exchange, "mode", "nccl") if world > 1 else "none (one process)"
     shares = {n: {"share": round(v["ms"] / total_ms, 4), "us_per_iter": round(v["ms"] * 1e3 / 4, 2),
@@ -557,7 +579,8 @@ def run_ours(args) -> None:
                    "swap_interval": args.swap_interval},
         "setup": {"parallelism": f"one discriminator worker per GPU x{args.gpus}, generator on rank 0",
                   "precision": args.precision, "cuda_graph": graphed, "exchange": exchange_mode,
-                  "swaps_in_timed_window": leg["swaps"],
+                  "swaps_in_timed_window": leg["swaps"], "push": push_mode, "per_rank_ms": leg["per_rank_ms"],
+                  "exchange_us_per_rank_eager": exchange_us,
                   "l2": "512 MB buffer written between timed iterations (outside the per-step event pairs)",
                   "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,

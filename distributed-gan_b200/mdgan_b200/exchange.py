@@ -147,9 +147,11 @@ class PeerExchange(Exchange):
         import os
 
         self.X_mc = None
+        self.push_mode = "peer stores (one per destination)"
         mc_ptr = int(getattr(hx, "multicast_ptr", 0) or 0)
         if proc == 0 and mc_ptr != 0 and os.environ.get("MDGAN_PEER_MULTICAST", "1") != "0":
             self.X_mc = _tensor_at(mc_ptr, tuple(self.X.shape), device)
+            self.push_mode = "NVSwitch multicast (multimem.st)"
         if proc == 0:
             self.x_addrs = torch.tensor([int(p) for p in hx.buffer_ptrs], dtype=torch.int64).to(device)
             self.sig_addrs = torch.tensor([int(hg.buffer_ptrs[p]) for p in range(1, n_procs)] or [0],
