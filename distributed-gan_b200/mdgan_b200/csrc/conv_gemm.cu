@@ -458,7 +458,7 @@ struct ConvTaSmem {
   static constexpr int kBStages = 4;
   static constexpr int kAStages = BN > 64 ? 4 : 3;
 #else
-  static constexpr int kBStages = BN > 64 ? 3 : 4;
+  static constexpr int kBStages = 4;                    // 4 x 32 KB weight stages + 4 x 16 KB raw stages = 192 KB at BN = 128
   static constexpr int kAStages = BN > 64 ? 2 : 3;      // TMEM stages of [A_hi (32 columns) | A_lo (32 columns)]
 #endif
   static constexpr int kBOff = kRawStages * kRawBytes;

@@ -13,6 +13,9 @@ repetition, dumps the offending tensor's diff statistics and keeps going (counts
 
     python tools/stress_conv.py --dataset CIFAR10 --n 128 --reps 5000 --save /tmp/ref.pt      # e.g. MDGAN_CONV_TA=0
     python tools/stress_conv.py --dataset CIFAR10 --n 128 --reps 5000 --against /tmp/ref.pt   # default kernels
+Cross-variant comparisons need the variants that change the ARITHMETIC switched off on both sides
+(MDGAN_BN_FUSED_STATS=0: the fused epilogue stores dy instead of da; MDGAN_CONV_UP2=0: the paired-parity kernel sums the
+taps in another order); the kernels that only move operands differently (TA / TG / TMA) must then agree bit for bit.
 Also checks the first repetition's generated batch against the fp64 CPU module (the test's 1e-3 bar, reported).
 """
 import argparse
