@@ -386,26 +386,28 @@ __device__ __forceinline__ float act_grad(float y, int act, float slope) {
   return 1.f;
 }
 
-// Stage 3: out = act(x*scale + shift)
-__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, float* __restrict__ out,
-                                int Pg, int C, long long total4, int act, float slope, int round_tf32) {
+// Stage 3: out = act(x*scale + shift).  One float4 per thread and step, grid-stride; the (row, channel, pass) of an
+// element comes from 32-bit divisions (the tensors of this path hold < 2^31 elements: checked by the launcher) -- the
+// 64-bit div / mod of the first version cost more instructions than the memory traffic they indexed.
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, float* __restrict__ out, int Pg, int C,
+                long long total4, int act, float slope, int round_tf32) {
   pdl_enter();
-  long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i4 >= total4) return;
-  const long long e = i4 * 4;
-  const int c = e % C;
-  const int g = (e / C) / Pg;
-  const float* st = stats + (long long)g * 4 * C;
-  const float4 v = *reinterpret_cast<const float4*>(x + e);
-  const float4 sc = *reinterpret_cast<const float4*>(st + 2 * C + c);
-  const float4 sh = *reinterpret_cast<const float4*>(st + 3 * C + c);
-  float4 o;
-  o.x = act_fwd(fmaf(v.x, sc.x, sh.x), act, slope);
-  o.y = act_fwd(fmaf(v.y, sc.y, sh.y), act, slope);
-  o.z = act_fwd(fmaf(v.z, sc.z, sh.z), act, slope);
-  o.w = act_fwd(fmaf(v.w, sc.w, sh.w), act, slope);
-  if (round_tf32) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
-  *reinterpret_cast<float4*>(out + e) = o;
+  const unsigned C4 = (unsigned)C >> 2, n4 = (unsigned)total4, stride = gridDim.x * blockDim.x;
+  for (unsigned i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += stride) {
+    const unsigned row = i4 / C4, c = (i4 - row * C4) << 2, g = row / (unsigned)Pg;
+    const float* st = stats + (size_t)g * 4 * C;
+    const float4 v = reinterpret_cast<const float4*>(x)[i4];
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(st + 2 * C + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(st + 3 * C + c));
+    float4 o;
+    o.x = act_fwd(fmaf(v.x, sc.x, sh.x), act, slope);
+    o.y = act_fwd(fmaf(v.y, sc.y, sh.y), act, slope);
+    o.z = act_fwd(fmaf(v.z, sc.z, sh.z), act, slope);
+    o.w = act_fwd(fmaf(v.w, sc.w, sh.w), act, slope);
+    if (round_tf32) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
+    reinterpret_cast<float4*>(out)[i4] = o;
+  }
 }
 
 // Backward statistics (same grid / last-block scheme as bn_stats_kernel): dy = da * act'(y); per channel
@@ -464,35 +466,38 @@ bn_bwd_stats_kernel(const float* __restrict__ da, const float* __restrict__ x, c
   }
 }
 
-// Backward stage 3: dx = scale * (dy - mean(dy) - xhat * mean(dy*xhat))
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ x,
-                                    const float* __restrict__ stats, const float* __restrict__ sums,
-                                    float* __restrict__ dx, int Pg, int C, long long total4, int act, float slope,
-                                    int round_tf32) {
+// Backward stage 3: dx = scale * (dy - mean(dy) - xhat * mean(dy*xhat))   (32-bit index math, grid-stride: see bn_apply)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ x, const float* __restrict__ stats,
+                    const float* __restrict__ sums, float* __restrict__ dx, int Pg, int C, long long total4, int act,
+                    float slope, int round_tf32) {
   pdl_enter();
-  long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i4 >= total4) return;
-  const long long e = i4 * 4;
-  const int c = e % C;
-  const int g = (e / C) / Pg;
-  const float* st = stats + (long long)g * 4 * C + c;
-  const float* sm = sums + (long long)g * 2 * C + c;
-  const float4 xv = *reinterpret_cast<const float4*>(x + e);
-  const float4 dv = *reinterpret_cast<const float4*>(da + e);
-  const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-  const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
-  float o[4];
+  const unsigned C4 = (unsigned)C >> 2, n4 = (unsigned)total4, stride = gridDim.x * blockDim.x;
   const float invP = 1.f / (float)Pg;
+  for (unsigned i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += stride) {
+    const unsigned row = i4 / C4, c = (i4 - row * C4) << 2, g = row / (unsigned)Pg;
+    const float* st = stats + (size_t)g * 4 * C + c;
+    const float* sm = sums + (size_t)g * 2 * C + c;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i4];
+    const float4 dv = reinterpret_cast<const float4*>(da)[i4];
+    const float4 mean4 = __ldg(reinterpret_cast<const float4*>(st)), istd4 = __ldg(reinterpret_cast<const float4*>(st + C));
+    const float4 sc4 = __ldg(reinterpret_cast<const float4*>(st + 2 * C)), sh4 = __ldg(reinterpret_cast<const float4*>(st + 3 * C));
+    const float4 s14 = __ldg(reinterpret_cast<const float4*>(sm)), s24 = __ldg(reinterpret_cast<const float4*>(sm + C));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+    const float mean[4] = {mean4.x, mean4.y, mean4.z, mean4.w}, istd[4] = {istd4.x, istd4.y, istd4.z, istd4.w};
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+    const float s1[4] = {s14.x, s14.y, s14.z, s14.w}, s2[4] = {s24.x, s24.y, s24.z, s24.w};
+    float o[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float mean = st[j], invstd = st[C + j], sc = st[2 * C + j], sh = st[3 * C + j];
-    const float y = fmaf(xs[j], sc, sh);
-    const float dy = ds[j] * act_grad(y, act, slope);
-    const float xhat = (xs[j] - mean) * invstd;
-    o[j] = sc * (dy - sm[j] * invP - xhat * (sm[C + j] * invP));
-    if (round_tf32) o[j] = to_tf32(o[j]);
+    for (int j = 0; j < 4; ++j) {
+      const float y = fmaf(xs[j], sc[j], sh[j]);
+      const float dy = ds[j] * act_grad(y, act, slope);
+      const float xhat = (xs[j] - mean[j]) * istd[j];
+      o[j] = sc[j] * (dy - s1[j] * invP - xhat * (s2[j] * invP));
+      if (round_tf32) o[j] = to_tf32(o[j]);
+    }
+    reinterpret_cast<float4*>(dx)[i4] = make_float4(o[0], o[1], o[2], o[3]);
   }
-  *reinterpret_cast<float4*>(dx + e) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // Backward twin of bn_finalize_kernel: partial slices hold the column sums of dy and of dy * xhat reduced by the
@@ -544,31 +549,35 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int phases, int row_ti
 }
 
 // dx = scale * (dy - mean(dy) - xhat * mean(dy * xhat)) with dy already gated by the activation (see above)
-__global__ void bn_bwd_apply_dy_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                       const float* __restrict__ stats, const float* __restrict__ sums,
-                                       float* __restrict__ dx, int Pg, int C, long long total4, int round_tf32) {
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_dy_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats,
+                       const float* __restrict__ sums, float* __restrict__ dx, int Pg, int C, long long total4,
+                       int round_tf32) {
   pdl_enter();
-  long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i4 >= total4) return;
-  const long long e = i4 * 4;
-  const int c = e % C;
-  const int g = (e / C) / Pg;
-  const float* st = stats + (long long)g * 4 * C + c;
-  const float* sm = sums + (long long)g * 2 * C + c;
-  const float4 xv = *reinterpret_cast<const float4*>(x + e);
-  const float4 dv = *reinterpret_cast<const float4*>(dy + e);
-  const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-  const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
-  float o[4];
+  const unsigned C4 = (unsigned)C >> 2, n4 = (unsigned)total4, stride = gridDim.x * blockDim.x;
   const float invP = 1.f / (float)Pg;
+  for (unsigned i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += stride) {
+    const unsigned row = i4 / C4, c = (i4 - row * C4) << 2, g = row / (unsigned)Pg;
+    const float* st = stats + (size_t)g * 4 * C + c;
+    const float* sm = sums + (size_t)g * 2 * C + c;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i4];
+    const float4 dv = reinterpret_cast<const float4*>(dy)[i4];
+    const float4 mean4 = __ldg(reinterpret_cast<const float4*>(st)), istd4 = __ldg(reinterpret_cast<const float4*>(st + C));
+    const float4 sc4 = __ldg(reinterpret_cast<const float4*>(st + 2 * C));
+    const float4 s14 = __ldg(reinterpret_cast<const float4*>(sm)), s24 = __ldg(reinterpret_cast<const float4*>(sm + C));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+    const float mean[4] = {mean4.x, mean4.y, mean4.z, mean4.w}, istd[4] = {istd4.x, istd4.y, istd4.z, istd4.w};
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
+    const float s1[4] = {s14.x, s14.y, s14.z, s14.w}, s2[4] = {s24.x, s24.y, s24.z, s24.w};
+    float o[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float mean = st[j], invstd = st[C + j], sc = st[2 * C + j];
-    const float xhat = (xs[j] - mean) * invstd;
-    o[j] = sc * (ds[j] - sm[j] * invP - xhat * (sm[C + j] * invP));
-    if (round_tf32) o[j] = to_tf32(o[j]);
+    for (int j = 0; j < 4; ++j) {
+      const float xhat = (xs[j] - mean[j]) * istd[j];
+      o[j] = sc[j] * (ds[j] - s1[j] * invP - xhat * (s2[j] * invP));
+      if (round_tf32) o[j] = to_tf32(o[j]);
+    }
+    reinterpret_cast<float4*>(dx)[i4] = make_float4(o[0], o[1], o[2], o[3]);
   }
-  *reinterpret_cast<float4*>(dx + e) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // dz = da * act'(a) for an activation with no BatchNorm in front (a = act(z); sign(a) == sign(z) for slope > 0).
@@ -781,6 +790,11 @@ __global__ void sum_slices_kernel(const float* __restrict__ in, float* __restric
 using namespace mdgan;
 
 static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+// BatchNorm apply kernels: grid-stride, at most 8 blocks of 256 threads per SM (two to four float4 per thread at b = 64)
+static inline unsigned bn_apply_blocks(long long total4) {
+  const unsigned b = blocks_for(total4, 256);
+  return b < 148u * 8u ? b : 148u * 8u;
+}
 
 extern "C" int mdgan_pack_weights(const float* W, float* out, int mode, int N, int C, int N_pad, int C_pad, int KK,
                                   int split, void* stream) {
@@ -852,7 +866,8 @@ extern "C" int mdgan_bn_forward(const float* x, float* out, const float* gamma, 
   MDGAN_LAUNCH(bn_stats_kernel, dim3(G * cpg, C / 32), dim3(256), 0, st, x, workspace, counters, gamma, beta, running_mean,
                running_var, num_batches_tracked, stats, G, Pg, C, cpg, rpc, eps, momentum);
   const long long total4 = (long long)G * Pg * C / 4;
-  MDGAN_LAUNCH(bn_apply_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, x, stats, out, Pg, C, total4, act, slope,
+  if (total4 >= (1LL << 29)) return MDGAN_ERR_UNSUPPORTED;   // 32-bit element indices in the apply kernels
+  MDGAN_LAUNCH(bn_apply_kernel, dim3(bn_apply_blocks(total4)), dim3(256), 0, st, x, stats, out, Pg, C, total4, act, slope,
                round_tf32);
   return 0;
 }
@@ -876,7 +891,8 @@ extern "C" int mdgan_bn_apply(const float* x, const float* stats, float* out, in
   if (!x || !stats || !out) return MDGAN_ERR_BAD_ARG;
   if (C % 4 != 0 || G < 1 || Pg < 1) return MDGAN_ERR_UNSUPPORTED;
   const long long total4 = (long long)G * Pg * C / 4;
-  MDGAN_LAUNCH(bn_apply_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, (cudaStream_t)stream, x, stats, out, Pg, C,
+  if (total4 >= (1LL << 29)) return MDGAN_ERR_UNSUPPORTED;
+  MDGAN_LAUNCH(bn_apply_kernel, dim3(bn_apply_blocks(total4)), dim3(256), 0, (cudaStream_t)stream, x, stats, out, Pg, C,
                total4, act, slope, round_tf32);
   return 0;
 }
@@ -892,7 +908,8 @@ extern "C" int mdgan_bn_backward(const float* da, const float* x, const float* s
   MDGAN_LAUNCH(bn_bwd_stats_kernel, dim3(G * cpg, C / 32), dim3(256), 0, st, da, x, stats, workspace, counters, sums, dgamma,
                dbeta, G, Pg, C, cpg, rpc, act, slope);
   const long long total4 = (long long)G * Pg * C / 4;
-  MDGAN_LAUNCH(bn_bwd_apply_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, da, x, stats, sums, dx, Pg, C, total4,
+  if (total4 >= (1LL << 29)) return MDGAN_ERR_UNSUPPORTED;
+  MDGAN_LAUNCH(bn_bwd_apply_kernel, dim3(bn_apply_blocks(total4)), dim3(256), 0, st, da, x, stats, sums, dx, Pg, C, total4,
                act, slope, round_tf32);
   return 0;
 }
@@ -912,7 +929,8 @@ extern "C" int mdgan_bn_bwd_apply_dy(const float* dy, const float* x, const floa
   if (!dy || !x || !stats || !sums || !dx) return MDGAN_ERR_BAD_ARG;
   if (C % 4 != 0 || G < 1 || Pg < 1) return MDGAN_ERR_UNSUPPORTED;
   const long long total4 = (long long)G * Pg * C / 4;
-  MDGAN_LAUNCH(bn_bwd_apply_dy_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, (cudaStream_t)stream, dy, x, stats, sums,
+  if (total4 >= (1LL << 29)) return MDGAN_ERR_UNSUPPORTED;
+  MDGAN_LAUNCH(bn_bwd_apply_dy_kernel, dim3(bn_apply_blocks(total4)), dim3(256), 0, (cudaStream_t)stream, dy, x, stats, sums,
                dx, Pg, C, total4, round_tf32);
   return 0;
 }
