@@ -540,6 +540,9 @@ conv_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   pdl_wait();
 
   static_assert(TG >= 1 && TG <= 2 && (TMA_A || TG == 1), "transposer groups: the loader warps double as transposers only when TMA feeds the tile");
+  // a group's consecutive K steps are TG apart: it must not get more than one barrier phase ahead on any stage (an
+  // mbarrier parity wait cannot tell two phases apart) -- three groups over two TMEM stages dead-locked in round 2
+  static_assert(TG <= S::kAStages && TG <= S::kRawStages, "transposer groups must not outnumber the stages they cycle through");
   if (warp < 12) {
     if (warp < 4 * TG) {
       // ---------------------------------------------------------------- transposers: raw stage -> TMEM A stage

@@ -38,10 +38,14 @@ constexpr int kWK = 32;  // pixels per stage
 constexpr int kWProducerWarps = 8;
 constexpr int kWThreads = (kWProducerWarps + 1) * 32;
 constexpr int kWPrefetch = 3;  // K steps of operand loads kept in flight in registers per producer thread
-// 2 groups: 62-74 us per CelebA b=64 layer; 4 groups: 57-66 us, but three of six benchmark processes started right after
-// another GPU process stalled with that build (round 2, gpurun calls 9-11; never with 2 groups) -- not understood, so 2.
+// 2 groups: 62-74 us per CelebA b=64 layer; 4 groups: 57-66 us.  A group may run at most ONE barrier phase ahead of the
+// MMAs on any stage, because an mbarrier parity wait cannot tell "the phase I need" from "two phases earlier": group g's
+// consecutive steps are kHiGroups apart, so it can be kHiGroups / kStages phases ahead on a stage -- the number of groups
+// must not exceed the number of stages (static_assert in the kernel).  Round 2 first ran 4 groups over 3 stages: one
+// benchmark process in five dead-locked (a group passed the `empty` wait of a stage whose previous contents had not
+// been consumed yet); 2 groups over 3 stages and 4 over 4 are safe by this argument and never stalled.
 #ifndef MDGAN_WGRAD_HI_GROUPS
-#define MDGAN_WGRAD_HI_GROUPS 2
+#define MDGAN_WGRAD_HI_GROUPS 4
 #endif
 constexpr int kHiGroups = MDGAN_WGRAD_HI_GROUPS;  // producer-warp groups of the TMEM-operand kernel (see its Hi producers)
 
@@ -292,7 +296,7 @@ template <int BN>
 struct WgradTaSmem {
   static constexpr int kBBytes = (BN / 32) * kWK * 128;   // one of hi / lo
   static constexpr int kStageBytes = 2 * kBBytes;         // [B_hi | B_lo]
-  static constexpr int kStages = 3;
+  static constexpr int kStages = 4;                       // >= kHiGroups (see MDGAN_WGRAD_HI_GROUPS)
   static constexpr int kRawBytes = (kWM / 32) * kWK * 128;  // 16 KB raw Lo tile
   static constexpr int kRawStages = 4;
   static constexpr int kAStages = BN > 64 ? 2 : 3;        // TMEM stages of [A_hi (32 columns) | A_lo (32 columns)]
@@ -395,6 +399,7 @@ wgrad_gemm_ta_kernel(const __grid_constant__ CUtensorMap tmap_lo, const WgradPar
     // outstanding memory operation of the thread; with loads prefetched several K steps ahead (round 1) each step
     // stalled for a full L2 round trip (~1.2 us per K step measured, 3x the MMA time).  Here no load is in flight at the
     // fence, and a group's load latency (~1.3 us under load) is covered by the other groups' steps.
+    static_assert(kHiGroups <= S::kStages, "a producer group may be at most one barrier phase ahead on a stage");
     constexpr int kGroupWarps = kWProducerWarps / kHiGroups, kGroupThreads = 32 * kGroupWarps;
     const int grp = (warp - kProd0) / kGroupWarps;
     const int tid = threadIdx.x - (kProd0 + kGroupWarps * grp) * 32;  // inside the group
