@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU call: smoke gate, suite, race hunt across kernel variants, transposer-group timing, parity report.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi -L | head -2
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2c1_smoke.log 2>&1 || { tail -30 gpurun_out/r2c1_smoke.log; echo SMOKE FAILED; exit 1; }

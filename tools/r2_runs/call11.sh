@@ -1,6 +1,6 @@
 #!/bin/bash
 # wgrad transposer groups + PDL re-test on the current build.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 WGRAD_BENCH_ONLY=wgrad timeout 60 python tools/conv_bench.py 1 > $O/r2c11_cb_tg1.log 2>&1
 MDGAN_WGRAD_TG=2 WGRAD_BENCH_ONLY=wgrad timeout 60 python tools/conv_bench.py 1 > $O/r2c11_cb_tg2.log 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # BatchNorm apply kernels with 32-bit index math: correctness + timing.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 ( timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_nets_gpu.py tests/test_mdgan_gpu.py -q -x 2>&1 | tail -4 ) > $O/r2c12_pytest.log; tail -2 $O/r2c12_pytest.log
 for i in 1 2; do

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU call 3 (lean): smoke gate, suite, bench variants, parity numbers.  Every command under a short timeout.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 180 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2c3_smoke.log 2>&1 || { tail -30 gpurun_out/r2c3_smoke.log; echo SMOKE FAILED; }
 tail -2 gpurun_out/r2c3_smoke.log | cut -c1-400

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Pipeline-depth experiment: default library vs the deep variant (4 A stages in TMEM + 4 weight stages on 128-wide tiles).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 DEEP=$PWD/distributed-gan_b200/mdgan_b200/libmdgan_b200_deep.so
 timeout 100 python tools/conv_bench.py 1 > $O/r2c5_convbench_default.log 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # elect.sync MMA/TMA issue roles: correctness + timing.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 180 python -c "import __graft_entry__ as g; g.smoke()" > $O/r2c6_smoke.log 2>&1 || { tail -30 $O/r2c6_smoke.log; echo SMOKE FAILED; exit 1; }
 tail -1 $O/r2c6_smoke.log | cut -c1-300

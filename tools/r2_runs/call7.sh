@@ -1,6 +1,6 @@
 #!/bin/bash
 # After the elect.sync fix: do transposer groups / pipeline depth matter now?
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 DEEP=$PWD/distributed-gan_b200/mdgan_b200/libmdgan_b200_deep.so
 timeout 100 python tools/conv_bench.py 1 > $O/r2c7_cb_tg1.log 2>&1

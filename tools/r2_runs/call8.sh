@@ -1,6 +1,6 @@
 #!/bin/bash
 # wgrad producer restructure (no loads in flight at the proxy fence): correctness + timing.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 WGRAD_BENCH_ONLY=wgrad timeout 100 python tools/conv_bench.py 1 > $O/r2c8_convbench.log 2>&1; cat $O/r2c8_convbench.log
 ( timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 ) > $O/r2c8_pytest.log; tail -3 $O/r2c8_pytest.log

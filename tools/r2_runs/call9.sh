@@ -1,6 +1,6 @@
 #!/bin/bash
 # wgrad producer groups 2 / 4 / 8 + PDL re-test.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 L=$PWD/distributed-gan_b200/mdgan_b200
 for v in default hi2 hi8; do

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Stall hunt for the shipped build: N benchmark processes back to back, each dumps its Python stack after 30 s
 # (faulthandler) and is killed at 45 s.  usage: gpu_r2_hunt.sh [runs]
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 RUNS=${1:-8}
 ( timeout 300 python -m pytest tests/test_kernels_gpu.py tests/test_nets_gpu.py -q -x 2>&1 | tail -3 ) > $O/r2h_pytest.log; tail -2 $O/r2h_pytest.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Multi-GPU validation: usage gpu_r2_mg.sh N   (N = 2 or 8 GPUs)
 N=${1:-2}
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 nvidia-smi -L | wc -l

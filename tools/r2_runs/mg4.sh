@@ -1,7 +1,7 @@
 #!/bin/bash
 # BASELINE config 3: CIFAR-10 shape, K = 4 workers on 4 GPUs, discriminator swap every iteration inside the timed window.
 N=4
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 250 $TR --master-port 29631 bench.py --gpus $N --dataset CIFAR10 --swap-interval 1 --steps 20 --warmup 5 --no-shapes > $O/r2mg4_cifar_swap1.json 2> $O/r2mg4_cifar_swap1.err; echo "rc=$?"; tail -2 $O/r2mg4_cifar_swap1.err | cut -c1-300

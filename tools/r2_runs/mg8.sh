@@ -1,7 +1,7 @@
 #!/bin/bash
 # 8-GPU validation (expensive: keep it short).
 N=8
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 nvidia-smi -L | wc -l

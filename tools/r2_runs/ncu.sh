@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 profiling call: launch list of the benchmark workload + ncu --set full of one iteration's GEMM kernels +
 # DRAM metrics of the bandwidth kernels.  Reports are exported to CSV on the box (gpurun_out is capped at 64 MiB).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 CMD="python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-shapes"
 timeout 300 $CMD > $O/r02_plain.log 2>&1 || { tail -20 $O/r02_plain.log; exit 1; }
