@@ -541,7 +541,9 @@ def run_ours(args) -> None:
     e2e = {"value": n_workers * 1e3 / e2e_ms, "unit": UNIT, "generator_it_s": 1e3 / e2e_ms, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(local),
            "api": "MDGANEngine.iteration (the loop body of actors.server.start / actors.worker.start): host torch RNG "
-                  "noise + host DataLoader batches -> pinned -> device, losses read back every iteration"}
+                  "noise + host DataLoader batches -> pinned -> device, losses read back every iteration; the host staging "
+                  "and the H2D copy of step i+1 run while step i computes (copy stream -> shadow buffers, adopted "
+                  "device-to-device at the start of step i+1; MDGAN_PREFETCH_H2D=0 uploads on the compute stream)"}
     engine.close()
     del engine
 

@@ -21,6 +21,7 @@ no CPU product path.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -110,6 +111,16 @@ class MDGANEngine:
         self.graph = None
         self._uploaded = None
         self._staged = False
+        # MDGAN_PREFETCH_H2D = 1 (default) | 0: with prefetch_host, the NEXT iteration's inputs are also copied to the
+        # device while the current iteration runs (copy stream -> shadow buffers; the iteration then starts with two
+        # device-to-device copies instead of waiting for PCIe).  See upload_ahead / upload_inputs.
+        self._h2d_ahead = (cfg.prefetch_host and device.type == "cuda"
+                           and os.environ.get("MDGAN_PREFETCH_H2D", "1") == "1")
+        self._copy_stream = None
+        self._ahead = False          # the shadow buffers hold the next iteration's inputs
+        self._ahead_ready = None     # copy stream: shadow buffers written
+        self._consumed = None        # compute stream: shadow buffers copied into the live input buffers
+        self.z_next = torch.zeros((kb, cfg.z_dim), **f) if (self._h2d_ahead and proc == 0) else None
         self.iterations_done = 0
 
     # ------------------------------------------------------------------------------------------ phases
@@ -132,9 +143,42 @@ class MDGANEngine:
             if stage is not None:
                 stage()
 
+    def upload_ahead(self) -> None:
+        """Pinned staging -> SHADOW device buffers on the copy stream, while the compute stream still runs the current
+        iteration (whose live input buffers must not change under it).  The copy stream first waits until the previous
+        shadow contents were consumed; the staging buffers are free again once its copies are done (`_uploaded`)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._ahead_ready = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+            if self._uploaded is None:
+                self._uploaded = torch.cuda.Event()
+        cs = self._copy_stream
+        cs.wait_event(self._consumed)
+        with torch.cuda.stream(cs):
+            if self.proc == 0 and self.cfg.z_source == "host":
+                self.z_next.copy_(self.z_host, non_blocking=True)
+            for n in self.local:
+                self.real_sources[n].upload_ahead()
+            self._uploaded.record(cs)
+            self._ahead_ready.record(cs)
+        self._ahead = True
+
     def upload_inputs(self) -> None:
         """Pinned staging -> device (async copies on the compute stream, always launched eagerly so that an event can
-        mark the moment the staging buffers are free again)."""
+        mark the moment the staging buffers are free again).  When `upload_ahead` already moved this iteration's
+        inputs to the device: wait for the copy stream and adopt the shadow buffers (device-to-device)."""
+        if self._ahead:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(self._ahead_ready)
+            if self.proc == 0 and self.cfg.z_source == "host":
+                self.z.copy_(self.z_next, non_blocking=True)
+            for n in self.local:
+                self.real_sources[n].adopt()
+            self._consumed.record(cur)
+            self._ahead = False
+            return
         if self.proc == 0 and self.cfg.z_source == "host":
             self.z.copy_(self.z_host, non_blocking=True)
         for n in self.local:
@@ -156,6 +200,8 @@ class MDGANEngine:
         self._staged = False
         self.stage_inputs()
         self._staged = True
+        if self._h2d_ahead and all(hasattr(self.real_sources[n], "upload_ahead") for n in self.local):
+            self.upload_ahead()
 
     def generate(self, staged: bool = False) -> None:
         """staged=False: also runs the host staging and the uploads (one call per phase, as the actors use it)."""

@@ -50,6 +50,7 @@ class _DeviceBatches:
         self.stream, self.device = stream, device
         self.pinned = torch.empty((stream.batch_size, *shape), dtype=torch.float32, pin_memory=True)
         self.dev = torch.empty((stream.batch_size, *shape), dtype=torch.float32, device=device)
+        self.next_dev = torch.empty_like(self.dev)   # shadow of `dev` for the early upload (upload_ahead / adopt)
 
     def stage(self) -> None:
         """Host half: next batch of the reference-order loader into the pinned buffer."""
@@ -58,6 +59,15 @@ class _DeviceBatches:
     def upload(self) -> None:
         """H2D from the pinned buffer (async on the current stream)."""
         self.dev.copy_(self.pinned, non_blocking=True)
+
+    def upload_ahead(self) -> None:
+        """H2D of the NEXT iteration's batch into a shadow buffer (called on the engine's copy stream while the
+        current iteration still reads `dev`), MDGANEngine.upload_ahead."""
+        self.next_dev.copy_(self.pinned, non_blocking=True)
+
+    def adopt(self) -> None:
+        """Shadow buffer -> the fixed buffer the (graph-captured) step reads; device-to-device on the compute stream."""
+        self.dev.copy_(self.next_dev, non_blocking=True)
 
     def __call__(self) -> torch.Tensor:
         return self.dev

@@ -100,3 +100,43 @@ def test_standalone_matches_oracle(tmp_path, monkeypatch):
     assert list(g.keys()) == list(oracle.G.state_dict().keys()) and list(d.keys()) == list(oracle.D.state_dict().keys())
     assert l2err(flat(g), flat(oracle.G.state_dict())) <= FREE_TOL["weights_l2"]
     assert l2err(flat(d), flat(oracle.D.state_dict())) <= FREE_TOL["weights_l2"]
+
+
+def test_bootstrap_on_mnist_files(tmp_path, monkeypatch):
+    """Real-data ingest end to end: bootstrap.py trains from MNIST-format files on disk through the
+    real torchvision.datasets.MNIST class (tests/mnist_files.py writes them; no --synthetic), streamed host batches,
+    early upload, phase graphs, a swap -- against the oracle on the same dataset object.  The shard is 3 batches long, so
+    the 4 iterations also cross the loader's epoch boundary (worker.py:162-167)."""
+    import bootstrap
+    import torchvision
+
+    from mnist_files import write_mnist_idx
+    from oracle.mdgan_oracle import OracleMDGAN
+
+    N, b, epochs = 2, 8, 4
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.delenv("MDGAN_SYNTH_M", raising=False)
+    monkeypatch.setenv("MDGAN_PRECISION", "tf32x3")
+    write_mnist_idx(tmp_path / "data" / "mnist", N * 3 * b, 16)
+    bootstrap.main(["--backend", "nccl", "--world_size", str(N + 1), "--ranks", f"0..{N}", "--dataset", "MNIST_DCGAN",
+                    "--epochs", str(epochs), "--local_epochs", "1", "--swap_interval", "2", "--device", "cuda",
+                    "--batch_size", str(b), "--iid", "1", "--seed", "3", "--beta_1", "0.5", "--generator_lr", "0.0002",
+                    "--discriminator_lr", "0.0002", "--log_interval", "1000", "--gpus", "1",
+                    "--master_addr", "127.0.0.1", "--master_port", "29534"])
+    mod = plugin("MNIST_DCGAN")
+    part = mod.Partitioner(N + 1, 0)
+    part.load_data()
+    assert isinstance(part.train_dataset, torchvision.datasets.MNIST) and len(part.train_dataset) == N * 3 * b
+    oracle = OracleMDGAN(mod.Generator, mod.Discriminator, part.train_dataset, N, b, mod.Z_DIM, mod.SHAPE, seed=3,
+                         beta_1=0.5, swap_interval=2)
+    ref = [oracle.step(e, record=False) for e in range(epochs)]
+    flat = lambda sd: torch.cat([v.reshape(-1).double() for k, v in sd.items() if v.dtype == torch.float32 and "running" not in k])
+    g = torch.load(tmp_path / "weights" / "generator_final.pt")
+    assert l2err(flat(g), flat(oracle.G.state_dict())) <= FREE_TOL["weights_l2"]
+    for n in range(N):
+        d = torch.load(tmp_path / "weights" / f"worker_{n + 1}" / "discriminator.pth")
+        assert l2err(flat(d), flat(oracle.D[n].state_dict())) <= FREE_TOL["weights_l2"]
+        rows = list(csv.DictReader(open(tmp_path / "logs" / f"mdgan.{N}.MNIST_DCGAN.worker.{n + 1}.logs.csv")))
+        assert len(rows) == epochs
+        for e, row in enumerate(rows):   # a wrong or stale real batch moves the loss by O(1), far outside this bound
+            assert abs(float(row["mean_d_loss"]) - ref[e]["mean_d_loss"][n]) <= FREE_TOL["loss"] * abs(ref[e]["mean_d_loss"][n])

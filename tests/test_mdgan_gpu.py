@@ -73,3 +73,50 @@ def test_engine_refuses_cpu_and_mlp():
         CudaNetFactory(torch.device("cpu"))
     with pytest.raises(UnsupportedModelError):
         extract_plan(plugin("MNIST").Discriminator(), "discriminator", (1, 28, 28))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_early_upload_is_bit_identical(monkeypatch, graph):
+    """The early upload (MDGAN_PREFETCH_H2D: next iteration's noise + real batches copied to shadow device buffers on
+    a copy stream while the current iteration runs, engine.upload_ahead) must not change a single bit: same host RNG
+    order, same batches, same step -- against the run that uploads on the compute stream at the start of every
+    iteration.  Streamed host batches, two workers in one process, a swap (across which nothing is prefetched)."""
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200 import routing
+    from mdgan_b200.engine import EngineConfig, MDGANEngine
+    from mdgan_b200.node import _DeviceBatches
+    from parity import build_actor_modules
+    from util import plugin
+
+    mod = plugin("CIFAR10")
+    N, b, epochs = 2, 16, 7
+    dev = torch.device("cuda", 0)
+    data = SyntheticImages(mod.SHAPE, N * 4 * b)
+    final = {}
+    for ahead in ("1", "0"):
+        monkeypatch.setenv("MDGAN_PREFETCH_H2D", ahead)
+        g, discs = build_actor_modules(mod, N, 3)
+        cfg = EngineConfig(n_workers=N, batch_size=b, z_dim=mod.Z_DIM, image_shape=tuple(mod.SHAPE), swap_interval=3,
+                           z_source="host", prefetch_host=True)
+        shards = routing.split_dataset(len(data), N, True)
+        src = {n: _DeviceBatches(routing.RealBatchStream(data, shards[n], b), dev, tuple(mod.SHAPE)) for n in range(N)}
+        eng = MDGANEngine(cfg, 0, 1, dev, g, discs, src)
+        assert eng._h2d_ahead == (ahead == "1")
+        used = 0
+        for e in range(epochs):
+            if graph and e == 2:
+                eng.capture()
+            eng.stage_inputs()
+            used += int(eng._ahead)
+            eng.device_iteration()
+            eng.prefetch_next(e, last=(e == epochs - 1))
+            eng.maybe_swap(e)
+            eng.mean_d_loss()   # the per-iteration read-back of the actors (synchronises)
+        expect = sum(1 for e in range(epochs - 1) if not routing.swap_due(e, 3, N))   # never across a swap draw
+        assert used == (expect if ahead == "1" else 0) and expect == 5
+        torch.cuda.synchronize()
+        final[ahead] = [eng.gen.state.state_f32.clone(), eng.gen.state.m.clone()] + \
+                       [eng.disc[n].state.state_f32.clone() for n in range(N)] + [eng.d_loss.clone(), eng.g_loss.clone()]
+        eng.close()
+    for a, c in zip(final["1"], final["0"]):
+        assert torch.equal(a, c)
