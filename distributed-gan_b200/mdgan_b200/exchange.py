@@ -37,6 +37,7 @@ class Exchange:
         # graph-captured ones on one NCCL communicator: a host-side (gloo) group for the pair table, which is host
         # data anyway, and a second device group for the state exchange.
         self.ctl_group = self.swap_group = None
+        self._swap_staging: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}   # per hosted worker, allocated once
         if n_procs > 1:
             self.ctl_group = dist.new_group(backend="gloo")
             self.swap_group = dist.new_group()
@@ -79,6 +80,15 @@ class Exchange:
         dist.broadcast(buf, src=0, group=self.ctl_group)
         return buf
 
+    def _staging(self, n: int, f32: torch.Tensor, i64: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Receive / scratch buffers of worker n's swap (the size of its flat state), kept across swaps: the swap is
+        on the loop's critical path every `swap_interval` iterations and must not go through the allocator."""
+        st = self._swap_staging.get(n)
+        if st is None or st[0].shape != f32.shape or st[1].shape != i64.shape or st[0].device != f32.device:
+            st = (torch.empty_like(f32), torch.empty_like(i64))
+            self._swap_staging[n] = st
+        return st
+
     # ---- C6
     def swap_states(self, local_states: Dict[int, Tuple[torch.Tensor, torch.Tensor]], pairs: torch.Tensor) -> List[int]:
         """local_states: {0-based worker index -> (state_f32, state_i64)} of the workers hosted here.
@@ -91,9 +101,11 @@ class Exchange:
             pn = partners[n + 1] - 1
             f32, i64 = local_states[n]
             if pn in local_states:
-                if n < pn:  # both hosted here: swap through clones
+                if n < pn:  # both hosted here: swap through the staging pair
                     of32, oi64 = local_states[pn]
-                    tf, ti = f32.clone(), i64.clone()
+                    tf, ti = self._staging(n, f32, i64)
+                    tf.copy_(f32)
+                    ti.copy_(i64)
                     f32.copy_(of32)
                     i64.copy_(oi64)
                     of32.copy_(tf)
@@ -101,7 +113,7 @@ class Exchange:
                 changed.append(n)
                 continue
             peer = routing.process_of_worker(pn, self.n_procs, self.n_workers)
-            rf, ri = torch.empty_like(f32), torch.empty_like(i64)
+            rf, ri = self._staging(n, f32, i64)
             # message order between two processes: by the SENDING worker's index on both sides
             ops.append((n, dist.P2POp(dist.isend, f32, peer, group=self.swap_group)))
             ops.append((n, dist.P2POp(dist.isend, i64, peer, group=self.swap_group)))
