@@ -188,6 +188,7 @@ def build_modules(mod, workers, seed):
         bootstrap._seed_actor(seed + n + 1)
         d = mod.Discriminator().to(dtype=torch.float32)
         d.apply(bootstrap._weights_init)
+        d._mdgan_rng_state = torch.get_rng_state()
         discs[n] = d
     return discs
 

@@ -93,6 +93,9 @@ def init_process(proc: int, args, n_procs: int, partitioner, image_shape, z_dim,
         _seed_actor(args.seed + n + 1)
         d = discriminator_cls().to(dtype=torch.float32)
         d.apply(_weights_init)
+        # the worker actor's global RNG stream goes on from here in the reference (its dropout draws, MNIST.py:89-94);
+        # several actors share this process, so the stream's state travels with the model (mlp_nets.MlpDiscNet)
+        d._mdgan_rng_state = torch.get_rng_state()
         discs[n + 1] = d
     device = torch.device(args.device)
     if proc == 0:

@@ -1,10 +1,11 @@
 """MNIST plugin with the reference's MLP models (/root/reference/src/datasets/MNIST.py:74-120: four Linear
-layers, LeakyReLU(0.2), always-active functional dropout 0.3).
+layers per net, LeakyReLU(0.2), always-active functional dropout 0.3 in the discriminator).
 
-The plugin loads and its models run under stock PyTorch (the oracle / CPU baseline use them), but the B200 engine
-covers the DCGAN conv family only and refuses this model loudly (`UnsupportedModelError`, no fallback): the MLP is
-not a dense-conv hot path and its dropout masks come from each worker's global RNG stream, which has no
-bit-compatible device equivalent.  Use `--dataset MNIST_DCGAN` for MNIST-shape runs on the GPU.
+The B200 engine runs this family on its own kernels (mdgan_b200/mlp_nets.py, csrc/mlp.cu: fp32 SGEMM with the
+bias / activation / dropout / gate tail fused).  The dropout masks are drawn on the host from each worker's torch RNG
+stream in the reference's call order and uploaded with the iteration's inputs, so they are the reference's masks bit
+for bit (tests/test_mlp_host.py, tests/test_mlp_gpu.py).  `--dataset MNIST_DCGAN` is the MNIST-shape DCGAN that
+BASELINE.json's configs 1/2 name.
 """
 from typing import Tuple
 

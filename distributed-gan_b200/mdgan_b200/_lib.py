@@ -54,6 +54,10 @@ SIGNATURES = {
     "mdgan_thin_up": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mdgan_thin_wgrad_slices": (_i, [_i, _i, _i]),
     "mdgan_thin_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "mdgan_sgemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _f, _p, _f, _p, _f, _i, _p]),
+    "mdgan_col_sum": (_i, [_p, _p, _i, _i, _p]),
+    "mdgan_linear_head_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "mdgan_linear_head_backward": (_i, [_p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _i, _p]),
 }
 
 

@@ -1,0 +1,227 @@
+// CUDA-core fp32 kernels for the reference's MLP plugin (datasets/MNIST.py:74-120: four Linear layers per net,
+// LeakyReLU(0.2), always-active dropout(0.3) in the discriminator, tanh / sigmoid outputs).  One iteration of that model
+// is ~2.4 GFLOP at b = 64 (F_D = 1.29, F_G = 1.13 GFLOP) in GEMMs of 64..128 rows: a 128-row tensor-core
+// tile would be half padding and tf32x3 would buy nothing over plain fp32 FMA, so the Linear layers run as a
+// register-blocked fp32 SGEMM with the layer's elementwise tail fused into the epilogue:
+//
+//   forward   y = x W^T + b -> LeakyReLU / tanh -> dropout (keep mask drawn on the HOST from the worker's torch RNG in
+//             the reference's order, so the masks are the reference's masks bit for bit: F.dropout on the CPU is
+//             noise = empty_like(x).bernoulli_(1 - p).div_(1 - p); x * noise)
+//   data grad dx = dy W, times the previous layer's dropout mask and LeakyReLU gate (torch's order: dropout backward,
+//             then leaky_relu backward)
+//   weight grad dW = dy^T x (PyTorch [out, in] layout, written straight into the flat gradient buffer), db = column sums
+//   head      Linear(L -> 1) + sigmoid + BCELoss(mean) and its backward (worker.py:197-206,220-227), bias included.
+//
+// All sums run in a fixed order (k ascending per output element), so results are bitwise repeatable.
+#include "common.cuh"
+
+namespace mdgan {
+
+constexpr int kSgBM = 64, kSgBN = 64, kSgBK = 16;
+
+// C[m][n] (row-major, ld = N) = epilogue(sum_k A(m,k) * B(k,n)),  A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs].
+// 256 threads = 16 x 16; thread (tx, ty) owns rows ty + 16 i and columns tx + 16 j (i, j < 4): shared-memory reads are
+// broadcasts (rows) and 16 consecutive banks (columns), global stores 64-byte runs.
+// Epilogue order: + bias[n] -> act (2 LeakyReLU, 3 tanh) -> keep mask (mask ? v * mask_scale : 0) -> gate
+// (gate > 0 ? v : v * gate_slope) -> (+ C if accumulate).
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
+             long long a_rs, long long a_cs, long long b_rs, long long b_cs, const float* __restrict__ bias, int act,
+             float slope, const unsigned char* __restrict__ mask, float mask_scale, const float* __restrict__ gate,
+             float gate_slope, int accumulate) {
+  __shared__ float As[kSgBK][kSgBM + 1];
+  __shared__ float Bs[kSgBK][kSgBN + 1];
+  pdl_enter();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * kSgBM, n0 = blockIdx.x * kSgBN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_k_fast = a_cs == 1, b_k_fast = b_rs == 1 && b_cs != 1;
+  for (int k0 = 0; k0 < K; k0 += kSgBK) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = threadIdx.x + 256 * u;
+      // the index that is contiguous in memory varies fastest over the threads
+      const int am = a_k_fast ? idx / kSgBK : idx % kSgBM, ak = a_k_fast ? idx % kSgBK : idx / kSgBM;
+      const int gm = m0 + am, gk = k0 + ak;
+      As[ak][am] = (gm < M && gk < K) ? __ldg(A + gm * a_rs + gk * a_cs) : 0.f;
+      const int bn = b_k_fast ? idx / kSgBK : idx % kSgBN, bk = b_k_fast ? idx % kSgBK : idx / kSgBN;
+      const int gn = n0 + bn, gk2 = k0 + bk;
+      Bs[bk][bn] = (gn < N && gk2 < K) ? __ldg(B + gk2 * b_rs + gn * b_cs) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSgBK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty + 16 * i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= N) continue;
+      const long long o = (long long)m * N + n;
+      float v = acc[i][j];
+      if (bias) v += bias[n];
+      if (act == 2) v = v > 0.f ? v : v * slope;
+      else if (act == 3) v = tanhf(v);
+      if (mask) v = mask[o] ? v * mask_scale : 0.f;
+      if (gate) v = gate[o] > 0.f ? v : v * gate_slope;
+      if (accumulate) v += C[o];
+      C[o] = v;
+    }
+  }
+}
+
+// out[n] = sum_m x[m][n] (m ascending): bias gradients.
+__global__ void col_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N) {
+  pdl_enter();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int m = 0; m < M; ++m) acc += x[(long long)m * N + n];
+  out[n] = acc;
+}
+
+// logit[n] = <a[n, :], w> + bias; p = sigmoid(logit); per-sample BCE term (log clamp at -100); dlogit = dBCE/dlogit
+// including the 1/b of the mean.  One 256-thread block per sample; the last block to finish reduces the terms in a
+// fixed order: loss[g] = mean over the b samples of pass g (label[g]), loss[G] = their sum.  Same arithmetic as
+// head_fwd_kernel (elementwise.cu) with the bias of nn.Linear added.
+__global__ void __launch_bounds__(256)
+linear_head_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+                       const float* __restrict__ label, float* __restrict__ prob, float* __restrict__ loss_terms,
+                       float* __restrict__ dlogit, float* __restrict__ loss, unsigned int* __restrict__ counter, int b,
+                       int G, int L) {
+  __shared__ float red[8];
+  __shared__ bool last;
+  pdl_enter();
+  const int n = blockIdx.x;
+  const float* row = a + (long long)n * L;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < L; i += 256) acc = fmaf(row[i], __ldg(w + i), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float logit = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) logit += red[i];
+    if (bias) logit += bias[0];
+    const float y = label[n / b];
+    const float p = 1.f / (1.f + expf(-logit));
+    const float lp = fmaxf(logf(p), -100.f);
+    const float l1p = fmaxf(log1pf(-p), -100.f);
+    prob[n] = p;
+    loss_terms[n] = (y - 1.f) * l1p - y * lp;
+    const float pq = (1.f - p) * p;
+    dlogit[n] = ((p - y) / fmaxf(pq, 1e-12f)) * (1.f / (float)b) * pq;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *counter = 0;
+  float total = 0.f;
+  for (int g = 0; g < G; ++g) {
+    float t = 0.f;
+    for (int i = threadIdx.x; i < b; i += 256) t += __ldcg(loss_terms + g * b + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float sgl = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) sgl += red[wv];
+      sgl /= (float)b;
+      loss[g] = sgl;
+      total += sgl;
+    }
+  }
+  if (threadIdx.x == 0) loss[G] = total;
+}
+
+// da[n][l] = dlogit[n] * w[l], then the dropout mask and the LeakyReLU gate of the layer that produced a (a is its
+// post-dropout output: where the mask kept the element, sign(a) is the sign of the pre-activation);
+// dw[l] = sum_n dlogit[n] * a[n][l], dbias = sum_n dlogit[n] (both optional, n ascending).
+__global__ void linear_head_bwd_kernel(const float* __restrict__ a, const float* __restrict__ w,
+                                       const float* __restrict__ dlogit, const unsigned char* __restrict__ mask,
+                                       float mask_scale, float gate_slope, float* __restrict__ da, float* __restrict__ dw,
+                                       float* __restrict__ dbias, int n_total, int L) {
+  pdl_enter();
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const float wv = w[l];
+  float acc = 0.f, accb = 0.f;
+  for (int n = 0; n < n_total; ++n) {
+    const long long o = (long long)n * L + l;
+    const float d = dlogit[n], av = a[o];
+    float v = d * wv;
+    if (mask) v = mask[o] ? v * mask_scale : 0.f;
+    v = av > 0.f ? v : v * gate_slope;
+    da[o] = v;
+    acc = fmaf(d, av, acc);
+    accb += d;
+  }
+  if (dw) dw[l] = acc;
+  if (dbias && l == 0) dbias[0] = accb;
+}
+
+}  // namespace mdgan
+
+using namespace mdgan;
+
+extern "C" int mdgan_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int a_rs, int a_cs, int b_rs,
+                           int b_cs, const float* bias, int act, float slope, const unsigned char* mask, float mask_scale,
+                           const float* gate, float gate_slope, int accumulate, void* stream) {
+  if (!A || !B || !C || M < 1 || N < 1 || K < 1) return MDGAN_ERR_BAD_ARG;
+  if (act != 0 && act != 2 && act != 3) return MDGAN_ERR_UNSUPPORTED;
+  const dim3 grid((unsigned)ceil_div(N, kSgBN), (unsigned)ceil_div(M, kSgBM));
+  if (grid.y > 65535u) return MDGAN_ERR_UNSUPPORTED;
+  MDGAN_LAUNCH(sgemm_kernel, grid, dim3(256), 0, (cudaStream_t)stream, A, B, C, M, N, K, (long long)a_rs, (long long)a_cs,
+               (long long)b_rs, (long long)b_cs, bias, act, slope, mask, mask_scale, gate, gate_slope, accumulate);
+  return 0;
+}
+
+extern "C" int mdgan_col_sum(const float* x, float* out, int M, int N, void* stream) {
+  if (!x || !out || M < 1 || N < 1) return MDGAN_ERR_BAD_ARG;
+  MDGAN_LAUNCH(col_sum_kernel, dim3((unsigned)ceil_div(N, 128)), dim3(128), 0, (cudaStream_t)stream, x, out, M, N);
+  return 0;
+}
+
+extern "C" int mdgan_linear_head_forward(const float* a, const float* w, const float* bias, const float* label,
+                                         float* prob, float* loss_terms, float* dlogit, float* loss, void* counter, int G,
+                                         int b, int L, void* stream) {
+  if (!a || !w || !label || !prob || !loss_terms || !dlogit || !loss || !counter || G < 1 || b < 1 || L < 1)
+    return MDGAN_ERR_BAD_ARG;
+  MDGAN_LAUNCH(linear_head_fwd_kernel, dim3((unsigned)(G * b)), dim3(256), 0, (cudaStream_t)stream, a, w, bias, label, prob,
+               loss_terms, dlogit, loss, (unsigned int*)counter, b, G, L);
+  return 0;
+}
+
+extern "C" int mdgan_linear_head_backward(const float* a, const float* w, const float* dlogit, const unsigned char* mask,
+                                          float mask_scale, float gate_slope, float* da, float* dw, float* dbias,
+                                          int n_total, int L, void* stream) {
+  if (!a || !w || !dlogit || !da || n_total < 1 || L < 1) return MDGAN_ERR_BAD_ARG;
+  MDGAN_LAUNCH(linear_head_bwd_kernel, dim3((unsigned)ceil_div(L, 128)), dim3(128), 0, (cudaStream_t)stream, a, w, dlogit,
+               mask, mask_scale, gate_slope, da, dw, dbias, n_total, L);
+  return 0;
+}

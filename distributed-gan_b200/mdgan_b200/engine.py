@@ -64,12 +64,24 @@ class CudaNetFactory:
 
     def generator(self, module: nn.Module, cfg: EngineConfig, n_samples: int):
         from .nets import GenNet
+        from .plan import is_mlp
 
+        if is_mlp(module):   # the reference's Linear / LeakyReLU / dropout family (datasets/MNIST.py:74-120)
+            from .mlp_nets import MlpGenNet
+
+            return MlpGenNet(module, cfg.z_dim, cfg.image_shape, n_samples, self.device, cfg.generator_lr, cfg.beta_1,
+                             cfg.beta_2)
         return GenNet(module, cfg.z_dim, cfg.image_shape, n_samples, self.device, cfg.generator_lr, cfg.beta_1, cfg.beta_2)
 
     def discriminator(self, module: nn.Module, cfg: EngineConfig):
         from .nets import DiscNet
+        from .plan import is_mlp
 
+        if is_mlp(module):
+            from .mlp_nets import MlpDiscNet
+
+            return MlpDiscNet(module, cfg.image_shape, cfg.batch_size, self.device, cfg.discriminator_lr, cfg.beta_1,
+                              cfg.beta_2, local_epochs=cfg.local_epochs)
         return DiscNet(module, cfg.image_shape, cfg.batch_size, self.device, cfg.discriminator_lr, cfg.beta_1, cfg.beta_2)
 
 
@@ -114,8 +126,11 @@ class MDGANEngine:
         # MDGAN_PREFETCH_H2D = 1 (default) | 0: with prefetch_host, the NEXT iteration's inputs are also copied to the
         # device while the current iteration runs (copy stream -> shadow buffers; the iteration then starts with two
         # device-to-device copies instead of waiting for PCIe).  See upload_ahead / upload_inputs.
+        # Nets with host-staged inputs of their own (the MLP family's dropout masks, mlp_nets.MlpDiscNet.stage_host) use
+        # the plain upload.
         self._h2d_ahead = (cfg.prefetch_host and device.type == "cuda"
-                           and os.environ.get("MDGAN_PREFETCH_H2D", "1") == "1")
+                           and os.environ.get("MDGAN_PREFETCH_H2D", "1") == "1"
+                           and not any(hasattr(d, "stage_host") for d in self.disc.values()))
         self._copy_stream = None
         self._ahead = False          # the shadow buffers hold the next iteration's inputs
         self._ahead_ready = None     # copy stream: shadow buffers written
@@ -140,6 +155,9 @@ class MDGANEngine:
             self.z_host.copy_(torch.randn((kb, self.cfg.z_dim, 1, 1)).view(kb, self.cfg.z_dim))
         for n in self.local:
             stage = getattr(self.real_sources[n], "stage", None)
+            if stage is not None:
+                stage()
+            stage = getattr(self.disc[n], "stage_host", None)   # worker-side host draws (dropout masks, worker RNG)
             if stage is not None:
                 stage()
 
@@ -183,6 +201,9 @@ class MDGANEngine:
             self.z.copy_(self.z_host, non_blocking=True)
         for n in self.local:
             upload = getattr(self.real_sources[n], "upload", None)
+            if upload is not None:
+                upload()
+            upload = getattr(self.disc[n], "upload_host", None)
             if upload is not None:
                 upload()
         if self.device.type == "cuda":

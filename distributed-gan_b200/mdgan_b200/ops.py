@@ -18,7 +18,7 @@ from .torch_ops import ns as _K
 import os
 
 MODE_DOWN, MODE_UP, MODE_DENSE = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 TF32, TF32X3 = 0, 1
 _PRECISION_NAMES = {"tf32": TF32, "tf32x3": TF32X3}
 
@@ -476,3 +476,58 @@ def sum_slices(x, out, count: int, stride: int):
     _run("sum_slices", 1, 0, 4.0 * out.numel() * (count + 1),
          lambda: _K.sum_slices(x, out, out.numel(), count, stride))
     return out
+
+
+# ----------------------------------------------------------------------------- Linear layers (the reference's MLP plugin)
+def _sgemm(name, A, B, out, M, N, K, a_rs, a_cs, b_rs, b_cs, bias=None, act=ACT_NONE, slope=0.0, mask=None, mask_scale=1.0,
+           gate=None, gate_slope=1.0, accumulate=False):
+    if mask is not None and (mask.dtype != torch.uint8 or mask.numel() != M * N):
+        raise _lib.MdganLibraryError("sgemm: the dropout mask must be uint8 [M, N]")
+    if out.numel() != M * N or (gate is not None and gate.numel() != M * N) or (bias is not None and bias.numel() != N):
+        raise _lib.MdganLibraryError("sgemm: operand shapes do not match M, N")
+    _run(name, 1, 2.0 * M * N * K, 4.0 * (M * K + K * N + M * N),
+         lambda: _K.sgemm(A, B, out, M, N, K, a_rs, a_cs, b_rs, b_cs, bias, act, slope, mask, mask_scale, gate,
+                          gate_slope, int(accumulate)))
+    return out
+
+
+def linear_forward(x, W, bias, out, act=ACT_NONE, slope=0.0, mask=None, mask_scale=1.0):
+    """out [M, N] = dropout(act(x [M, K] @ W [N, K]^T + bias)); mask: uint8 keep mask [M, N] or None."""
+    M, K = x.shape
+    N = W.shape[0]
+    return _sgemm("linear_forward", x, W, out, M, N, K, K, 1, 1, K, bias=bias, act=act, slope=slope, mask=mask,
+                  mask_scale=mask_scale)
+
+
+def linear_dgrad(dy, W, out, gate=None, gate_slope=1.0, mask=None, mask_scale=1.0, accumulate=False):
+    """out [M, K] (+)= (dy [M, N] @ W [N, K]) through the dropout mask and LeakyReLU gate of the layer that produced the
+    [M, K] activations (gate = that layer's output)."""
+    M, N = dy.shape
+    K = W.shape[1]
+    return _sgemm("linear_dgrad", dy, W, out, M, K, N, N, 1, K, 1, mask=mask, mask_scale=mask_scale, gate=gate,
+                  gate_slope=gate_slope, accumulate=accumulate)
+
+
+def linear_wgrad(dy, x, dW):
+    """dW [N, K] = dy [M, N]^T @ x [M, K] (PyTorch Linear.weight layout)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    return _sgemm("linear_wgrad", dy, x, dW, N, K, M, 1, N, K, 1)
+
+
+def col_sum(x, out):
+    M, N = x.shape
+    _run("col_sum", 1, 0, 4.0 * (x.numel() + N), lambda: _K.col_sum(x, out, M, N))
+    return out
+
+
+def linear_head_forward(a, w, bias, label, prob, loss_terms, dlogit, loss, counter, G, b):
+    L = a.shape[1]
+    _run("head_forward", 1, 2.0 * G * b * L, 4.0 * (G * b * L + L),
+         lambda: _K.linear_head_forward(a, w, bias, label, prob, loss_terms, dlogit, loss, counter, G, b, L))
+
+
+def linear_head_backward(a, w, dlogit, da, dw, dbias, mask=None, mask_scale=1.0, gate_slope=1.0):
+    n, L = a.shape
+    _run("head_backward", 1, 4.0 * n * L, 4.0 * (2 * n * L + 2 * L),
+         lambda: _K.linear_head_backward(a, w, dlogit, mask, mask_scale, gate_slope, da, dw, dbias, n, L))

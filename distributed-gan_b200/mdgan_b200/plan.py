@@ -6,8 +6,9 @@ the plugin, /root/reference/src/bootstrap.py:75-76,102-103).  Plugins are writte
 forward), so instead of walking `children()` the plan is recorded from one dry-run forward on a tiny CPU batch
 under a TorchFunctionMode: every torch-level op (conv2d, conv_transpose2d, batch_norm, relu, leaky_relu, tanh,
 sigmoid, view/squeeze/flatten) is captured with the *parameter tensors it received*, which are mapped back to
-`state_dict` keys by identity.  Anything else (Linear, dropout, unknown strides) raises: there is no fallback
-path, unsupported models are refused loudly.
+`state_dict` keys by identity.  Anything else (unknown strides, unknown ops) raises: there is no fallback path,
+unsupported models are refused loudly.  `extract_mlp_plan` does the same for the reference's second model family, the
+Linear / LeakyReLU / dropout MLP of datasets/MNIST.py:74-120.
 
 The dry run restores the module's buffers (BatchNorm running stats / num_batches_tracked) and the global RNG
 state afterwards, so it is invisible to the training run.
@@ -242,3 +243,93 @@ def _validate(plan: NetPlan) -> None:
                 raise UnsupportedModelError("discriminator hidden layers must be Conv -> BatchNorm -> LeakyReLU")
         if L[-1].act != ACT_SIGMOID or L[-1].bias is not None or L[-1].bn is not None:
             raise UnsupportedModelError("discriminator head must be Conv(bias=False) -> sigmoid")
+
+
+# ------------------------------------------------------------------------------------------------ MLP family
+@dataclass
+class LinearLayer:
+    """One nn.Linear with the elementwise tail the reference applies to it (MNIST.py:86-96,114-120)."""
+    weight: str                # state_dict keys
+    bias: Optional[str]
+    n_in: int
+    n_out: int
+    act: str = ACT_NONE        # lrelu | tanh | sigmoid | none
+    slope: float = 0.0
+    drop_p: float = 0.0        # F.dropout(p, training=True) after the activation (always active in the reference)
+
+
+@dataclass
+class MlpPlan:
+    role: str
+    layers: List[LinearLayer] = field(default_factory=list)
+    in_shape: Tuple[int, ...] = ()
+    out_shape: Tuple[int, ...] = ()
+
+
+def is_mlp(module: nn.Module) -> bool:
+    """True for models made of nn.Linear layers only (no convolution): the reference's MNIST plugin."""
+    mods = list(module.modules())
+    return any(isinstance(m, nn.Linear) for m in mods) and not any(
+        isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.BatchNorm2d)) for m in mods)
+
+
+def extract_mlp_plan(module: nn.Module, role: str, in_shape: Tuple[int, ...]) -> MlpPlan:
+    """role "generator": in_shape = (z_dim, 1, 1), output reshaped to the image; role "discriminator": in_shape =
+    (C, H, W), flattened, one sigmoid output per sample."""
+    if any(p.device.type != "cpu" for p in module.parameters()):
+        raise UnsupportedModelError("extract_mlp_plan expects the module on the CPU (the engine owns the device copy)")
+    names = _param_names(module)
+    ops, out = record_ops(module, torch.zeros((2, *in_shape), dtype=torch.float32))
+    plan = MlpPlan(role=role, in_shape=tuple(in_shape), out_shape=tuple(out.shape[1:]))
+    cur: Optional[LinearLayer] = None
+    for name, args, kwargs, res in ops:
+        if name in _IGNORED:
+            continue
+        if name == "linear":
+            x, w = args[0], args[1]
+            b = _arg(args, kwargs, 2, "bias")
+            if x.dim() != 2 or names.get(id(w)) is None or (b is not None and names.get(id(b)) is None):
+                raise UnsupportedModelError("linear: expected a 2-D input and module parameters")
+            if cur is not None and cur.n_out != int(w.shape[1]):
+                raise UnsupportedModelError("linear layers must be chained")
+            cur = LinearLayer(weight=names[id(w)], bias=names[id(b)] if b is not None else None, n_in=int(w.shape[1]),
+                              n_out=int(w.shape[0]))
+            plan.layers.append(cur)
+        elif name in ("leaky_relu", "leaky_relu_", "tanh", "sigmoid"):
+            if cur is None or cur.act != ACT_NONE or cur.drop_p != 0.0:
+                raise UnsupportedModelError(f"{name}: activation must directly follow a Linear layer")
+            if name.startswith("leaky_relu"):
+                cur.act, cur.slope = ACT_LRELU, float(_arg(args, kwargs, 1, "negative_slope", 0.01))
+            else:
+                cur.act = ACT_TANH if name == "tanh" else ACT_SIGMOID
+        elif name == "dropout":
+            p = float(_arg(args, kwargs, 1, "p", 0.5))
+            training = bool(_arg(args, kwargs, 2, "training", True))
+            if cur is None or cur.act != ACT_LRELU or cur.drop_p != 0.0 or not (0.0 < p < 1.0):
+                raise UnsupportedModelError("dropout must follow Linear -> LeakyReLU with 0 < p < 1")
+            if training:   # F.dropout(x, p) defaults to training=True whatever module.training says (MNIST.py:89)
+                cur.drop_p = p
+        else:
+            raise UnsupportedModelError(f"op `{name}` is not supported by the B200 MD-GAN engine (MLP family: Linear, "
+                                        "LeakyReLU, dropout, tanh / sigmoid outputs; no fallback path exists)")
+    L = plan.layers
+    if len(L) < 2:
+        raise UnsupportedModelError("an MLP needs at least two Linear layers")
+    n_in = 1
+    for d in in_shape:
+        n_in *= d
+    if L[0].n_in != n_in:
+        raise UnsupportedModelError("the first Linear layer must take the flattened input")
+    for l in L[:-1]:
+        if l.act != ACT_LRELU or l.slope <= 0.0:
+            raise UnsupportedModelError("hidden layers must be Linear -> LeakyReLU(slope > 0) [-> dropout]")
+    if role == "generator":
+        n_out = 1
+        for d in plan.out_shape:
+            n_out *= d
+        if L[-1].act != ACT_TANH or L[-1].n_out != n_out or any(l.drop_p for l in L):
+            raise UnsupportedModelError("generator must end with Linear -> tanh reshaped to the image, without dropout")
+    else:
+        if L[-1].act != ACT_SIGMOID or L[-1].n_out != 1 or plan.out_shape != ():
+            raise UnsupportedModelError("discriminator must end with Linear(., 1) -> sigmoid -> flatten")
+    return plan

@@ -56,6 +56,13 @@ SPECS: Dict[str, str] = {
     "thin_down": "T img, T W, T! out, int n_img, int CI, int Hi, int Wi, int N, int act, float slope, int round_tf32",
     "thin_up": "T src, T W, T! out, int n_img, int H, int Wd, int C, int N, int act_tanh, int accumulate",
     "thin_wgrad": "T feat, T img, T! partial, int n_img, int CI, int Hl, int Wl, int C1",
+    "sgemm": "T A, T B, T! C, int M, int N, int K, int a_rs, int a_cs, int b_rs, int b_cs, T? bias, int act, float slope, "
+             "T? mask, float mask_scale, T? gate, float gate_slope, int accumulate",
+    "col_sum": "T x, T! out, int M, int N",
+    "linear_head_forward": "T a, T w, T? bias, T label, T! prob, T! loss_terms, T! dlogit, T! loss, T! counter, int G, "
+                           "int b, int L",
+    "linear_head_backward": "T a, T w, T dlogit, T? mask, float mask_scale, float gate_slope, T! da, T?! dw, T?! dbias, "
+                            "int n_total, int L",
 }
 
 _lib_handle = None

@@ -61,7 +61,7 @@ def build_parser() -> argparse.ArgumentParser:
 
 class Standalone:
     def __init__(self, dataset_module, dataset, batch_size: int, device: torch.device, seed: int, generator_lr: float,
-                 discriminator_lr: float, beta_1: float, beta_2: float):
+                 discriminator_lr: float, beta_1: float, beta_2: float, factory=None):
         from mdgan_b200.engine import CudaNetFactory, EngineConfig
 
         np.random.seed(seed)
@@ -76,9 +76,13 @@ class Standalone:
         self.it = iter(self.loader)
         cfg = EngineConfig(n_workers=1, batch_size=batch_size, z_dim=self.z_dim, image_shape=tuple(dataset_module.SHAPE),
                            generator_lr=generator_lr, discriminator_lr=discriminator_lr, beta_1=beta_1, beta_2=beta_2)
-        fac = CudaNetFactory(device)
+        fac = factory or CudaNetFactory(device)
         self.gen = fac.generator(self.G, cfg, batch_size)
         self.disc = fac.discriminator(self.D, cfg)
+        if hasattr(self.disc, "stage_host"):
+            # MLP plugin (datasets/MNIST.py): one process, ONE global RNG -- the dropout draws of the three discriminator
+            # forwards interleave with the noise draws on the same stream (standalone_gan.py:190-214)
+            self.disc.rng = torch.default_generator
         self.real_dev = torch.empty((batch_size, *dataset_module.SHAPE), device=device)
         self.z_dev = torch.empty((batch_size, self.z_dim), device=device)
 
@@ -90,6 +94,11 @@ class Standalone:
             real = next(self.it)[0]
         self.real_dev.copy_(real, non_blocking=True)
         self.z_dev.copy_(torch.randn(self.b, self.z_dim, 1, 1).view(self.b, self.z_dim), non_blocking=True)
+        if hasattr(self.disc, "stage_host"):
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()   # the previous step's mask upload has read the staging buffer
+            self.disc.stage_host()
+            self.disc.upload_host()
         fake = self.gen.forward(self.z_dev)
         d_loss = self.disc.train_step(self.real_dev, fake)
         g_loss = self.disc.feedback_step(fake)

@@ -175,6 +175,35 @@ int mdgan_head_forward(const float* a, const float* wt, const float* label, floa
 int mdgan_head_backward(const float* a, const float* wt, const float* dlogit, float* da, float* dw, int n_total, int HW,
                         int C, void* stream);
 
+/* ---- the reference's MLP plugin (datasets/MNIST.py:74-120) on CUDA cores --------------------------------------
+ * mdgan_sgemm: C [M][N] row-major = epilogue(sum_k A(m,k) B(k,n)) in fp32 FMA, k ascending (bitwise repeatable).
+ *   A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs] (element strides), which covers the three products of an
+ *   nn.Linear without a transposed copy:  forward y = x W^T (A = x, B(k,n) = W[n][k]);  data gradient dx = dy W;
+ *   weight gradient dW = dy^T x, written in the PyTorch [out][in] layout.
+ *   Epilogue, in this order: + bias[n] (optional) -> act (MDGAN_ACT_NONE / MDGAN_ACT_LRELU with `slope` /
+ *   MDGAN_ACT_TANH) -> dropout keep mask (optional uint8 [M][N]: kept elements times mask_scale = 1/(1-p), dropped
+ *   ones zero; the mask is drawn on the host from the worker's torch RNG in the reference's call order, so it equals
+ *   F.dropout's noise, MNIST.py:89-94) -> LeakyReLU-backward gate (optional fp32 [M][N]: the gated layer's output; v
+ *   where it is > 0, v * gate_slope elsewhere) -> += C (accumulate: the error feedback summed into its slot,
+ *   actors/worker.py:227-233).  Replaces nn.Linear + F.leaky_relu + F.dropout + torch.tanh MNIST.py:80-96,106-120 and
+ *   their autograd backward (actors/worker.py:204,227; actors/server.py:286-292).
+ * mdgan_col_sum: out[n] = sum_m x[m][n]: the bias gradients.
+ * mdgan_linear_head_forward / _backward: Linear(L,1) + sigmoid + BCELoss(mean) (MNIST.py:96, actors/worker.py:96,
+ *   199-204,222-227) with the conventions of mdgan_head_forward (label per pass, loss[G] = sum, dlogit includes 1/b,
+ *   counter zero before the first call); w [L] = Linear.weight [1][L], bias [1].  Backward: da = dlogit * w through the
+ *   dropout mask (optional) and the LeakyReLU gate of the layer that produced a; dw [L], dbias [1] optional. */
+#define MDGAN_ACT_TANH 3
+int mdgan_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int a_rs, int a_cs, int b_rs, int b_cs,
+                const float* bias, int act, float slope, const unsigned char* mask, float mask_scale, const float* gate,
+                float gate_slope, int accumulate, void* stream);
+int mdgan_col_sum(const float* x, float* out, int M, int N, void* stream);
+int mdgan_linear_head_forward(const float* a, const float* w, const float* bias, const float* label, float* prob,
+                              float* loss_terms, float* dlogit, float* loss, void* counter, int G, int b, int L,
+                              void* stream);
+int mdgan_linear_head_backward(const float* a, const float* w, const float* dlogit, const unsigned char* mask,
+                               float mask_scale, float gate_slope, float* da, float* dw, float* dbias, int n_total, int L,
+                               void* stream);
+
 /* ---- torch.optim.Adam on a flat parameter buffer (actors/server.py:111-113,308-312; actors/worker.py:97-99,206).
  * step_count points to two device int32: [0] the number of steps already taken (incremented on the device by the
  * last block of the launch), [1] a block counter that must be zero before the first call. */

@@ -98,6 +98,7 @@ def build_actor_modules(mod, n_workers: int, seed: int):
         bootstrap._seed_actor(seed + n + 1)
         d = mod.Discriminator().to(dtype=torch.float32)
         d.apply(bootstrap._weights_init)
+        d._mdgan_rng_state = torch.get_rng_state()   # as bootstrap.init_process does
         discs[n] = d
     bootstrap._seed_actor(seed)
     g = mod.Generator().to(dtype=torch.float32)

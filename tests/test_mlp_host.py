@@ -1,0 +1,148 @@
+"""Host logic of the MLP path (datasets/MNIST.py:74-120 on the engine) WITHOUT a GPU: the kernels are replaced by their
+plain-torch statements (tests/mlp_ref_ops.py), everything else is the product code -- plan extraction, mlp_nets
+(layer wiring, gradient routing, the dropout masks drawn from each worker's RNG stream in the reference's order),
+engine.MDGANEngine (staging, routing, feedback slots, swap).  Checked against the oracle and against the golden
+fixture of the UNMODIFIED reference's own MNIST run (tests/golden/mnist_n2.pt).  The CUDA kernels themselves are
+checked against the same plain-torch statements in tests/test_mlp_gpu.py."""
+from pathlib import Path
+
+import pytest
+import torch
+
+import mlp_ref_ops
+from parity import build_actor_modules, l2err
+from util import plugin
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+class _CpuMlpFactory:
+    def __init__(self, device):
+        self.device = device
+
+    def generator(self, module, cfg, n_samples):
+        from mdgan_b200.mlp_nets import MlpGenNet
+
+        return MlpGenNet(module, cfg.z_dim, cfg.image_shape, n_samples, self.device, cfg.generator_lr, cfg.beta_1, cfg.beta_2)
+
+    def discriminator(self, module, cfg):
+        from mdgan_b200.mlp_nets import MlpDiscNet
+
+        return MlpDiscNet(module, cfg.image_shape, cfg.batch_size, self.device, cfg.discriminator_lr, cfg.beta_1,
+                          cfg.beta_2, local_epochs=cfg.local_epochs)
+
+
+class _HostBatches:
+    def __init__(self, stream):
+        self.stream, self.cur = stream, None
+
+    def stage(self):
+        self.cur = self.stream.next().clone()
+
+    def __call__(self):
+        return self.cur
+
+
+def _engine(mod, dataset, N, b, swap, local_epochs=1, prefetch=False, seed=3):
+    from mdgan_b200 import routing
+    from mdgan_b200.engine import EngineConfig, MDGANEngine
+
+    g, discs = build_actor_modules(mod, N, seed)
+    cfg = EngineConfig(n_workers=N, batch_size=b, z_dim=mod.Z_DIM, image_shape=tuple(mod.SHAPE), swap_interval=swap,
+                       local_epochs=local_epochs, z_source="host", prefetch_host=prefetch)
+    shards = routing.split_dataset(len(dataset), N, True)
+    src = {n: _HostBatches(routing.RealBatchStream(dataset, shards[n], b)) for n in range(N)}
+    dev = torch.device("cpu")
+    return MDGANEngine(cfg, 0, 1, dev, g, discs, src, factory=_CpuMlpFactory(dev))
+
+
+@pytest.mark.parametrize("N,b,epochs,swap,local_epochs,prefetch", [
+    (2, 8, 4, 2, 1, False),
+    (2, 8, 4, 2, 1, True),      # masks of iteration e+1 drawn while e "runs": the worker streams must not care
+    (4, 4, 3, 1, 2, False),     # two local epochs: 12 + 3 mask draws per worker and iteration
+    (1, 16, 2, 10 ** 6, 1, False),
+])
+def test_mlp_engine_matches_oracle(monkeypatch, N, b, epochs, swap, local_epochs, prefetch):
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200 import ops
+    from oracle.mdgan_oracle import OracleMDGAN
+
+    mlp_ref_ops.patch(monkeypatch, ops)
+    torch.set_num_threads(1)
+    mod = plugin("MNIST")
+    data = SyntheticImages(mod.SHAPE, N * 4 * b)
+    eng = _engine(mod, data, N, b, swap, local_epochs, prefetch)
+    assert all(type(d).__name__ == "MlpDiscNet" for d in eng.disc.values()) and type(eng.gen).__name__ == "MlpGenNet"
+    oracle = OracleMDGAN(mod.Generator, mod.Discriminator, data, N, b, mod.Z_DIM, mod.SHAPE, seed=3, beta_1=0.5,
+                         swap_interval=swap, local_epochs=local_epochs)
+    for e in range(epochs):
+        eng.stage_inputs()
+        eng.device_iteration()
+        eng.prefetch_next(e, last=(e == epochs - 1))
+        pairs = eng.maybe_swap(e)
+        ref = oracle.step(e, record=True)
+        assert (pairs is None) == (ref["pairs"] is None) and (pairs is None or torch.equal(pairs, ref["pairs"]))
+        assert l2err(eng.X, ref["X"]) < 1e-5, e
+        for n in range(N):
+            assert abs(eng.mean_d_loss()[n] - ref["mean_d_loss"][n]) <= 1e-5 * abs(ref["mean_d_loss"][n]), (e, n)
+            assert abs(float(eng.g_loss[n]) - float(ref["loss_gen"][n])) <= 1e-5 * abs(float(ref["loss_gen"][n])), (e, n)
+    eng.sync_modules()
+    flat = lambda sd: torch.cat([v.reshape(-1).double() for v in sd.values()])
+    assert l2err(flat(eng.gen_module.state_dict()), flat(oracle.G.state_dict())) < 1e-4
+    for n in range(N):
+        assert list(eng.disc_modules[n].state_dict().keys()) == list(oracle.D[n].state_dict().keys())
+        assert l2err(flat(eng.disc_modules[n].state_dict()), flat(oracle.D[n].state_dict())) < 1e-4
+
+
+def test_mlp_engine_matches_the_references_own_run(monkeypatch):
+    """tests/golden/mnist_n2.pt: per-iteration mean_d_loss and final state_dicts of the UNMODIFIED reference
+    (bootstrap.py, 3 gloo processes, datasets/MNIST.py with its always-on dropout)."""
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200 import ops
+
+    mlp_ref_ops.patch(monkeypatch, ops)
+    torch.set_num_threads(1)
+    fx = torch.load(GOLDEN / "mnist_n2.pt", weights_only=False)
+    c = fx["case"]
+    assert c["dataset"] == "MNIST" and c["mode"] == "distributed"
+    mod = plugin("MNIST")
+    data = SyntheticImages(mod.SHAPE, c["samples"])
+    eng = _engine(mod, data, c["workers"], c["batch"], c["swap_interval"], seed=c["seed"])
+    for e in range(c["epochs"]):
+        eng.iteration(e, last=(e == c["epochs"] - 1))
+        for n in range(c["workers"]):
+            ref = fx["mean_d_loss"][n][e]
+            assert abs(eng.mean_d_loss()[n] - ref) <= 1e-5 * abs(ref), (e, n)
+    eng.sync_modules()
+    sd = eng.gen_module.state_dict()
+    assert list(sd.keys()) == list(fx["G"].keys())
+    for k, v in sd.items():
+        f = fx["G"][k]
+        sample = v.detach().reshape(-1)[::211]
+        assert (sample - f["sample"]).abs().max().item() <= 1e-5 * max(f["sample"].abs().max().item(), 1e-3), k
+
+
+def test_mlp_standalone_matches_oracle(monkeypatch):
+    """standalone_gan.py on the MLP plugin (BASELINE config 1's own model): ONE global RNG stream carries the loader
+    seeds, the noise and the nine dropout draws of every step, in the reference's order (standalone_gan.py:180-227)."""
+    import standalone_gan
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200 import ops
+    from oracle.mdgan_oracle import OracleStandalone
+
+    mlp_ref_ops.patch(monkeypatch, ops)
+    torch.set_num_threads(1)
+    mod = plugin("MNIST")
+    b, steps = 8, 5
+    data = SyntheticImages(mod.SHAPE, 3 * b)           # the loader wraps around inside the run
+    dev = torch.device("cpu")
+    run = standalone_gan.Standalone(mod, data, b, dev, 1, 2e-4, 2e-4, 0.5, 0.999, factory=_CpuMlpFactory(dev))
+    got = [tuple(float(x) for x in run.step()) for _ in range(steps)]
+    oracle = OracleStandalone(mod.Generator, mod.Discriminator, data, b, mod.Z_DIM, seed=1, beta_1=0.5)
+    for (d_loss, g_loss) in got:
+        ref = oracle.step()
+        assert abs(d_loss - ref["mean_d_loss"]) <= 1e-5 * abs(ref["mean_d_loss"])
+        assert abs(g_loss - ref["mean_g_loss"]) <= 1e-5 * abs(ref["mean_g_loss"])
+    run.gen.state.store_to(run.G)
+    flat = lambda sd: torch.cat([v.reshape(-1).double() for v in sd.values()])
+    assert l2err(flat(run.G.state_dict()), flat(oracle.G.state_dict())) < 1e-4
