@@ -69,7 +69,8 @@ def parse_args():
 
 
 def workload_name(args, n_workers: int, dataset=None, swap=None) -> str:
-    shape = {"MNIST_DCGAN": "MNIST-shape 1x28x28", "CIFAR10": "CIFAR-10-shape 3x32x32", "CelebA": "CelebA-shape 3x64x64"}
+    shape = {"MNIST_DCGAN": "MNIST-shape 1x28x28", "CIFAR10": "CIFAR-10-shape 3x32x32", "CelebA": "CelebA-shape 3x64x64",
+             "MNIST": "MNIST 1x28x28 reference MLP (Linear / LeakyReLU / dropout 0.3)"}
     swap = args.swap_interval if swap is None else swap
     swap_txt = f"discriminator swap every {swap} iteration(s) inside the timed window" if swap > 0 and n_workers > 1 \
         else "swap off in the timed window"
@@ -562,6 +563,20 @@ def run_ours(args) -> None:
                 "workload": workload_name(args, n_workers, ds_name, swap), "ms_per_step": sub["ms_per_step"],
                 "generator_it_s": 1e3 / sub["ms_per_step"], "value": n_workers * 1e3 / sub["ms_per_step"], "unit": UNIT,
                 "steps": sub_steps, "swaps_in_timed_window": sub["swaps"], "gpu_launches_per_step": sub["launches_per_step"]}
+        if world == 1:
+            # the reference's own MNIST plugin (MLP with always-on dropout; the host draws its masks every step,
+            # outside the per-step event pair like the other host staging; their upload is inside)
+            try:
+                eng, _, _, _, sub = device_leg("MNIST", 0, sub_steps, 3, False)
+                eng.close()
+                del eng
+                shapes[f"MNIST_MLP_b{b}"] = {
+                    "workload": workload_name(args, n_workers, "MNIST", 0).replace(" DCGAN,", ","),
+                    "ms_per_step": sub["ms_per_step"], "generator_it_s": 1e3 / sub["ms_per_step"],
+                    "value": n_workers * 1e3 / sub["ms_per_step"], "unit": UNIT, "steps": sub_steps,
+                    "swaps_in_timed_window": 0, "gpu_launches_per_step": sub["launches_per_step"]}
+            except Exception as e:  # noqa: BLE001 -- a sub-line must not take the headline down with it
+                shapes[f"MNIST_MLP_b{b}"] = {"error": repr(e)[:300]}
 
     if world > 1:
         dist.barrier()
