@@ -17,49 +17,82 @@
 
 namespace mdgan {
 
-constexpr int kSgBM = 64, kSgBN = 64, kSgBK = 16;
+constexpr int kSgBK = 16;
 
 // C[m][n] (row-major, ld = N) = epilogue(sum_k A(m,k) * B(k,n)),  A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs].
-// 256 threads = 16 x 16; thread (tx, ty) owns rows ty + 16 i and columns tx + 16 j (i, j < 4): shared-memory reads are
-// broadcasts (rows) and 16 consecutive banks (columns), global stores 64-byte runs.
+// BM x BN output tile per CTA, (BM/4) x (BN/4) threads, a 4 x 4 register tile per thread (rows 4 ty .. 4 ty + 3, columns
+// 4 tx .. 4 tx + 3), K stepped by 16 through shared memory ([k][m] / [k][n], rows padded to a multiple of 16 bytes so
+// that a thread fetches its four A and four B values of a k with ONE 128-bit load each: 2 LDS per 16 FMA).  The next
+// K tile's global loads are issued into registers before the current tile is consumed, so their latency overlaps the
+// FMAs.  The layers of this model family have 64 .. 128 rows (b, 2b): tiles of 32 x 32 (64 threads) keep ~130 CTAs in
+// flight on such shapes where 64 x 64 tiles would occupy 32 of the 148 SMs; 64 x 64 is used once it fills the machine
+// (the weight gradients).  The sum over k is sequential per output element in both configurations (k ascending, one
+// fmaf chain), so the result does not depend on the tile size.
 // Epilogue order: + bias[n] -> act (2 LeakyReLU, 3 tanh) -> keep mask (mask ? v * mask_scale : 0) -> gate
 // (gate > 0 ? v : v * gate_slope) -> (+ C if accumulate).
-__global__ void __launch_bounds__(256)
+template <int BM, int BN>
+__global__ void __launch_bounds__((BM / 4) * (BN / 4))
 sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
              long long a_rs, long long a_cs, long long b_rs, long long b_cs, const float* __restrict__ bias, int act,
              float slope, const unsigned char* __restrict__ mask, float mask_scale, const float* __restrict__ gate,
              float gate_slope, int accumulate) {
-  __shared__ float As[kSgBK][kSgBM + 1];
-  __shared__ float Bs[kSgBK][kSgBN + 1];
+  constexpr int THREADS = (BM / 4) * (BN / 4), TXN = BN / 4;
+  constexpr int LA = BM * kSgBK / THREADS, LB = BN * kSgBK / THREADS;   // global loads per thread and K tile
+  static_assert(BM % 4 == 0 && BN % 4 == 0 && (BM * kSgBK) % THREADS == 0 && (BN * kSgBK) % THREADS == 0, "tile shape");
+  __shared__ __align__(16) float As[kSgBK][BM + 4];
+  __shared__ __align__(16) float Bs[kSgBK][BN + 4];
   pdl_enter();
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * kSgBM, n0 = blockIdx.x * kSgBN;
+  const int tid = threadIdx.x;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // the index that is contiguous in memory varies fastest over the threads
   const bool a_k_fast = a_cs == 1, b_k_fast = b_rs == 1 && b_cs != 1;
-  for (int k0 = 0; k0 < K; k0 += kSgBK) {
+  float ra[LA], rb[LB];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = threadIdx.x + 256 * u;
-      // the index that is contiguous in memory varies fastest over the threads
-      const int am = a_k_fast ? idx / kSgBK : idx % kSgBM, ak = a_k_fast ? idx % kSgBK : idx / kSgBM;
+    for (int u = 0; u < LA; ++u) {
+      const int idx = tid + THREADS * u;
+      const int am = a_k_fast ? idx / kSgBK : idx % BM, ak = a_k_fast ? idx % kSgBK : idx / BM;
       const int gm = m0 + am, gk = k0 + ak;
-      As[ak][am] = (gm < M && gk < K) ? __ldg(A + gm * a_rs + gk * a_cs) : 0.f;
-      const int bn = b_k_fast ? idx / kSgBK : idx % kSgBN, bk = b_k_fast ? idx % kSgBK : idx / kSgBN;
-      const int gn = n0 + bn, gk2 = k0 + bk;
-      Bs[bk][bn] = (gn < N && gk2 < K) ? __ldg(B + gk2 * b_rs + gn * b_cs) : 0.f;
+      ra[u] = (gm < M && gk < K) ? __ldg(A + gm * a_rs + gk * a_cs) : 0.f;
     }
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int idx = tid + THREADS * u;
+      const int bn = b_k_fast ? idx / kSgBK : idx % BN, bk = b_k_fast ? idx % kSgBK : idx / BN;
+      const int gn = n0 + bn, gk = k0 + bk;
+      rb[u] = (gn < N && gk < K) ? __ldg(B + gk * b_rs + gn * b_cs) : 0.f;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < LA; ++u) {
+      const int idx = tid + THREADS * u;
+      const int am = a_k_fast ? idx / kSgBK : idx % BM, ak = a_k_fast ? idx % kSgBK : idx / BM;
+      As[ak][am] = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int idx = tid + THREADS * u;
+      const int bn = b_k_fast ? idx / kSgBK : idx % BN, bk = b_k_fast ? idx % kSgBK : idx / BN;
+      Bs[bk][bn] = rb[u];
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += kSgBK) {
+    stash();
     __syncthreads();
+    if (k0 + kSgBK < K) fetch(k0 + kSgBK);
 #pragma unroll
     for (int kk = 0; kk < kSgBK; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -69,11 +102,11 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty + 16 * i;
+    const int m = m0 + ty * 4 + i;
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx + 16 * j;
+      const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       const long long o = (long long)m * N + n;
       float v = acc[i][j];
@@ -94,7 +127,8 @@ __global__ void col_sum_kernel(const float* __restrict__ x, float* __restrict__ 
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float acc = 0.f;
-  for (int m = 0; m < M; ++m) acc += x[(long long)m * N + n];
+#pragma unroll 8
+  for (int m = 0; m < M; ++m) acc += x[(long long)m * N + n];   // loads independent, adds in order
   out[n] = acc;
 }
 
@@ -171,6 +205,7 @@ __global__ void linear_head_bwd_kernel(const float* __restrict__ a, const float*
   if (l >= L) return;
   const float wv = w[l];
   float acc = 0.f, accb = 0.f;
+#pragma unroll 4
   for (int n = 0; n < n_total; ++n) {
     const long long o = (long long)n * L + l;
     const float d = dlogit[n], av = a[o];
@@ -194,10 +229,19 @@ extern "C" int mdgan_sgemm(const float* A, const float* B, float* C, int M, int 
                            const float* gate, float gate_slope, int accumulate, void* stream) {
   if (!A || !B || !C || M < 1 || N < 1 || K < 1) return MDGAN_ERR_BAD_ARG;
   if (act != 0 && act != 2 && act != 3) return MDGAN_ERR_UNSUPPORTED;
-  const dim3 grid((unsigned)ceil_div(N, kSgBN), (unsigned)ceil_div(M, kSgBM));
-  if (grid.y > 65535u) return MDGAN_ERR_UNSUPPORTED;
-  MDGAN_LAUNCH(sgemm_kernel, grid, dim3(256), 0, (cudaStream_t)stream, A, B, C, M, N, K, (long long)a_rs, (long long)a_cs,
-               (long long)b_rs, (long long)b_cs, bias, act, slope, mask, mask_scale, gate, gate_slope, accumulate);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long big_tiles = (long long)ceil_div(N, 64) * ceil_div(M, 64);
+  if (big_tiles >= 148) {   // 64 x 64 tiles fill the machine
+    const dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
+    if (grid.y > 65535u) return MDGAN_ERR_UNSUPPORTED;
+    MDGAN_LAUNCH((sgemm_kernel<64, 64>), grid, dim3(256), 0, st, A, B, C, M, N, K, (long long)a_rs, (long long)a_cs,
+                 (long long)b_rs, (long long)b_cs, bias, act, slope, mask, mask_scale, gate, gate_slope, accumulate);
+  } else {
+    const dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32));
+    if (grid.y > 65535u) return MDGAN_ERR_UNSUPPORTED;
+    MDGAN_LAUNCH((sgemm_kernel<32, 32>), grid, dim3(64), 0, st, A, B, C, M, N, K, (long long)a_rs, (long long)a_cs,
+                 (long long)b_rs, (long long)b_cs, bias, act, slope, mask, mask_scale, gate, gate_slope, accumulate);
+  }
   return 0;
 }
 

@@ -81,7 +81,8 @@ class CudaNetFactory:
             from .mlp_nets import MlpDiscNet
 
             return MlpDiscNet(module, cfg.image_shape, cfg.batch_size, self.device, cfg.discriminator_lr, cfg.beta_1,
-                              cfg.beta_2, local_epochs=cfg.local_epochs)
+                              cfg.beta_2, local_epochs=cfg.local_epochs,
+                              mask_source="host" if cfg.z_source == "host" else "device")
         return DiscNet(module, cfg.image_shape, cfg.batch_size, self.device, cfg.discriminator_lr, cfg.beta_1, cfg.beta_2)
 
 
@@ -130,7 +131,7 @@ class MDGANEngine:
         # the plain upload.
         self._h2d_ahead = (cfg.prefetch_host and device.type == "cuda"
                            and os.environ.get("MDGAN_PREFETCH_H2D", "1") == "1"
-                           and not any(hasattr(d, "stage_host") for d in self.disc.values()))
+                           and not any(getattr(d, "stage_host", None) is not None for d in self.disc.values()))
         self._copy_stream = None
         self._ahead = False          # the shadow buffers hold the next iteration's inputs
         self._ahead_ready = None     # copy stream: shadow buffers written

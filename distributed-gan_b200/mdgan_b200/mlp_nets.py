@@ -34,8 +34,10 @@ def _keep_scale(p: float) -> float:
 class MlpDiscNet:
     def __init__(self, module: nn.Module, image_shape: Tuple[int, int, int], batch_size: int, device: torch.device,
                  lr: float, beta_1: float, beta_2: float, max_groups: int = 2, local_epochs: int = 1,
-                 rng_state: Optional[torch.Tensor] = None):
-        """rng_state: state of the worker actor's global torch RNG right after its model was built (bootstrap stores it
+                 rng_state: Optional[torch.Tensor] = None, mask_source: str = "host"):
+        """mask_source "host" (parity mode, see above) | "device": the keep masks come from the CUDA generator inside
+        the step (no host draw, no upload; what the reference does when it runs on a GPU) -- follows EngineConfig.z_source.
+        rng_state: state of the worker actor's global torch RNG right after its model was built (bootstrap stores it
         on the module as `_mdgan_rng_state`); default: this process' global RNG as it is now -- correct for a process
         that hosts exactly this one worker, like a reference worker process."""
         self.device, self.b, self.shape = device, batch_size, tuple(image_shape)
@@ -88,6 +90,11 @@ class MlpDiscNet:
         self.mask_fb = [p[0] for p in pairs]
         self._host_fb = [p[1] for p in pairs]
         self.has_dropout = per_row > 0
+        if mask_source not in ("host", "device"):
+            raise ValueError(f"mask_source must be 'host' or 'device', got {mask_source!r}")
+        self.mask_source = mask_source
+        if mask_source == "device":   # no host half at all (engine.stage_inputs / upload_inputs look these up)
+            self.stage_host = self.upload_host = None
         self.rng = torch.Generator()
         state = rng_state if rng_state is not None else getattr(module, "_mdgan_rng_state", None)
         self.rng.set_state(state.clone() if state is not None else torch.get_rng_state())
@@ -113,6 +120,13 @@ class MlpDiscNet:
     def upload_host(self) -> None:
         if self.has_dropout:
             self.mask_dev.copy_(self.mask_host, non_blocking=True)
+
+    def _draw_on_device(self, masks: List[Optional[torch.Tensor]]) -> None:
+        """mask_source == "device": Bernoulli(1 - p) keep masks from the CUDA generator (graph-capturable)."""
+        if self.mask_source == "device":
+            for m, ly in zip(masks, self.hidden):
+                if m is not None:
+                    m.bernoulli_(1.0 - ly.drop_p)
 
     # ------------------------------------------------------------------ parameters
     def repack(self) -> None:
@@ -171,6 +185,7 @@ class MlpDiscNet:
         masks = self.mask_train[min(self._le, self.local_epochs - 1)]
         self._le += 1
         x = self.img.view(self.nmax, self.n_in)[: 2 * b]
+        self._draw_on_device(masks)
         self.forward(x, 2, self.labels_train, masks)
         self.backward(x, 2, True, masks)
         self.adam()
@@ -181,6 +196,7 @@ class MlpDiscNet:
         """worker.py:220-233.  dBCE(D(X_g),1)/dX_g goes to `out` (default self.feedback; accumulate=True adds)."""
         self._le = 0   # the feedback pass closes the iteration
         x = x_g.reshape(self.b, self.n_in)
+        self._draw_on_device(self.mask_fb)
         self.forward(x, 1, self.labels_ones, self.mask_fb)
         self.backward(x, 1, False, self.mask_fb, out=out, accumulate=accumulate)
         return self.loss[0]

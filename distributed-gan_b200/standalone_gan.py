@@ -79,7 +79,7 @@ class Standalone:
         fac = factory or CudaNetFactory(device)
         self.gen = fac.generator(self.G, cfg, batch_size)
         self.disc = fac.discriminator(self.D, cfg)
-        if hasattr(self.disc, "stage_host"):
+        if getattr(self.disc, "stage_host", None) is not None:
             # MLP plugin (datasets/MNIST.py): one process, ONE global RNG -- the dropout draws of the three discriminator
             # forwards interleave with the noise draws on the same stream (standalone_gan.py:190-214)
             self.disc.rng = torch.default_generator
@@ -94,7 +94,7 @@ class Standalone:
             real = next(self.it)[0]
         self.real_dev.copy_(real, non_blocking=True)
         self.z_dev.copy_(torch.randn(self.b, self.z_dim, 1, 1).view(self.b, self.z_dim), non_blocking=True)
-        if hasattr(self.disc, "stage_host"):
+        if getattr(self.disc, "stage_host", None) is not None:
             if self.device.type == "cuda":
                 torch.cuda.current_stream(self.device).synchronize()   # the previous step's mask upload has read the staging buffer
             self.disc.stage_host()

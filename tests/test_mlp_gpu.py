@@ -161,6 +161,40 @@ def test_mlp_engine_matches_oracle_on_gpu(N, b, epochs, swap, local_epochs, grap
         assert l2err(flat(eng.disc_modules[n].state_dict()), flat(oracle.D[n].state_dict())) < 5e-3
 
 
+def test_mlp_device_mask_source():
+    """z_source = "device" (the throughput mode): noise AND dropout masks come from the CUDA generator inside the captured
+    step -- no host draw, no upload.  Not comparable sample for sample; checked for the keep rate, fresh masks on every
+    replay, and a finite, moving loss."""
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200 import routing
+    from mdgan_b200.engine import EngineConfig, MDGANEngine
+    from mdgan_b200.node import DeviceResidentBatches
+
+    mod = plugin("MNIST")
+    N, b = 2, 64
+    data = SyntheticImages(mod.SHAPE, N * 4 * b)
+    g, discs = build_actor_modules(mod, N, 3)
+    cfg = EngineConfig(n_workers=N, batch_size=b, z_dim=mod.Z_DIM, image_shape=tuple(mod.SHAPE), swap_interval=10 ** 9,
+                       z_source="device")
+    shards = routing.split_dataset(len(data), N, True)
+    src = {n: DeviceResidentBatches(routing.RealBatchStream(data, shards[n], b), DEV, tuple(mod.SHAPE), 4) for n in range(N)}
+    eng = MDGANEngine(cfg, 0, 1, DEV, g, discs, src)
+    net = eng.disc[0]
+    assert net.mask_source == "device" and net.stage_host is None
+    seen, losses = [], []
+    for e in range(6):
+        if e == 2:
+            eng.capture()
+        eng.iteration(e)
+        seen.append(net.mask_train[0][0].clone())
+        losses.append(eng.mean_d_loss()[0])
+    eng.close()
+    for m in seen:
+        assert abs(m.float().mean().item() - 0.7) < 0.01 and int(m.max()) == 1
+    assert all(not torch.equal(seen[i], seen[i + 1]) for i in range(5)), "every replay must draw fresh masks"
+    assert all(l == l and 0.1 < l < 10 for l in losses) and len(set(losses)) == 6
+
+
 def test_mlp_engine_matches_the_references_own_run_on_gpu():
     """tests/golden/mnist_n2.pt: the UNMODIFIED reference's MNIST run (per-iteration mean_d_loss, final generator)."""
     from datasets.DataPartitioner import SyntheticImages
