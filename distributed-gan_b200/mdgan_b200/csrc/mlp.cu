@@ -13,6 +13,8 @@
 //   head      Linear(L -> 1) + sigmoid + BCELoss(mean) and its backward (worker.py:197-206,220-227), bias included.
 //
 // All sums run in a fixed order (k ascending per output element), so results are bitwise repeatable.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mdgan {
@@ -100,6 +102,115 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
     }
     __syncthreads();
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      const long long o = (long long)m * N + n;
+      float v = acc[i][j];
+      if (bias) v += bias[n];
+      if (act == 2) v = v > 0.f ? v : v * slope;
+      else if (act == 3) v = tanhf(v);
+      if (mask) v = mask[o] ? v * mask_scale : 0.f;
+      if (gate) v = gate[o] > 0.f ? v : v * gate_slope;
+      if (accumulate) v += C[o];
+      C[o] = v;
+    }
+  }
+}
+
+// The 64 .. 128-row layers again, with K split over the warps of the CTA: 32 x 32 output tile, 256 threads = four groups
+// of 64 (8 x 8 threads, 4 x 4 register tile each); a K tile of 64 is loaded by all 256 threads (8 + 8 values each,
+// prefetched into registers one tile ahead) and group g multiplies its 16 k of the tile.  Against sgemm_kernel<32,32>
+// that is four times the warps per SM and four times the bytes in flight per exposed global-memory latency, and a
+// quarter as many of those exposures (784 / 64 = 13 tiles instead of 49).  The four partial tiles are combined through
+// shared memory in a fixed order ((g0 + g1) + g2) + g3 by group 0, which also runs the epilogue: bitwise repeatable; the
+// last bits differ from the single-chain sum of the other configurations.  MDGAN_SGEMM_SPLITK=0 selects
+// sgemm_kernel<32,32> instead.
+constexpr int kSkBM = 32, kSkBN = 32, kSkBK = 64, kSkGroups = 4, kSkThreads = 256;
+
+__global__ void __launch_bounds__(kSkThreads)
+sgemm_splitk_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
+                    long long a_rs, long long a_cs, long long b_rs, long long b_cs, const float* __restrict__ bias, int act,
+                    float slope, const unsigned char* __restrict__ mask, float mask_scale, const float* __restrict__ gate,
+                    float gate_slope, int accumulate) {
+  constexpr int LA = kSkBM * kSkBK / kSkThreads, LB = kSkBN * kSkBK / kSkThreads, KG = kSkBK / kSkGroups;
+  __shared__ __align__(16) float As[kSkBK][kSkBM + 4];
+  __shared__ __align__(16) float Bs[kSkBK][kSkBN + 4];
+  __shared__ float red[kSkGroups - 1][64][17];
+  pdl_enter();
+  const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
+  const int tx = t & 7, ty = t >> 3;
+  const int m0 = blockIdx.y * kSkBM, n0 = blockIdx.x * kSkBN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_k_fast = a_cs == 1, b_k_fast = b_rs == 1 && b_cs != 1;
+  float ra[LA], rb[LB];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < LA; ++u) {
+      const int idx = tid + kSkThreads * u;
+      const int am = a_k_fast ? idx / kSkBK : idx % kSkBM, ak = a_k_fast ? idx % kSkBK : idx / kSkBM;
+      const int gm = m0 + am, gk = k0 + ak;
+      ra[u] = (gm < M && gk < K) ? __ldg(A + gm * a_rs + gk * a_cs) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int idx = tid + kSkThreads * u;
+      const int bn = b_k_fast ? idx / kSkBK : idx % kSkBN, bk = b_k_fast ? idx % kSkBK : idx / kSkBN;
+      const int gn = n0 + bn, gk = k0 + bk;
+      rb[u] = (gn < N && gk < K) ? __ldg(B + gk * b_rs + gn * b_cs) : 0.f;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < LA; ++u) {
+      const int idx = tid + kSkThreads * u;
+      const int am = a_k_fast ? idx / kSkBK : idx % kSkBM, ak = a_k_fast ? idx % kSkBK : idx / kSkBM;
+      As[ak][am] = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int idx = tid + kSkThreads * u;
+      const int bn = b_k_fast ? idx / kSkBK : idx % kSkBN, bk = b_k_fast ? idx % kSkBK : idx / kSkBN;
+      Bs[bk][bn] = rb[u];
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += kSkBK) {
+    stash();
+    __syncthreads();
+    if (k0 + kSkBK < K) fetch(k0 + kSkBK);
+#pragma unroll
+    for (int kk = 0; kk < KG; ++kk) {
+      const int k = g * KG + kk;
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  if (g > 0) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) red[g - 1][t][e] = acc[e >> 2][e & 3];
+  }
+  __syncthreads();
+  if (g > 0) return;
+#pragma unroll
+  for (int gg = 0; gg < kSkGroups - 1; ++gg)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e >> 2][e & 3] += red[gg][t][e];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
@@ -237,10 +348,18 @@ extern "C" int mdgan_sgemm(const float* A, const float* B, float* C, int M, int 
     MDGAN_LAUNCH((sgemm_kernel<64, 64>), grid, dim3(256), 0, st, A, B, C, M, N, K, (long long)a_rs, (long long)a_cs,
                  (long long)b_rs, (long long)b_cs, bias, act, slope, mask, mask_scale, gate, gate_slope, accumulate);
   } else {
+    static const bool split_k = [] {
+      const char* e = getenv("MDGAN_SGEMM_SPLITK");
+      return !(e && e[0] == '0');
+    }();
     const dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32));
     if (grid.y > 65535u) return MDGAN_ERR_UNSUPPORTED;
-    MDGAN_LAUNCH((sgemm_kernel<32, 32>), grid, dim3(64), 0, st, A, B, C, M, N, K, (long long)a_rs, (long long)a_cs,
-                 (long long)b_rs, (long long)b_cs, bias, act, slope, mask, mask_scale, gate, gate_slope, accumulate);
+    if (split_k)
+      MDGAN_LAUNCH(sgemm_splitk_kernel, grid, dim3(kSkThreads), 0, st, A, B, C, M, N, K, (long long)a_rs, (long long)a_cs,
+                   (long long)b_rs, (long long)b_cs, bias, act, slope, mask, mask_scale, gate, gate_slope, accumulate);
+    else
+      MDGAN_LAUNCH((sgemm_kernel<32, 32>), grid, dim3(64), 0, st, A, B, C, M, N, K, (long long)a_rs, (long long)a_cs,
+                   (long long)b_rs, (long long)b_cs, bias, act, slope, mask, mask_scale, gate, gate_slope, accumulate);
   }
   return 0;
 }
