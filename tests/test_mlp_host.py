@@ -4,12 +4,19 @@ plain-torch statements (tests/mlp_ref_ops.py), everything else is the product co
 engine.MDGANEngine (staging, routing, feedback slots, swap).  Checked against the oracle and against the golden
 fixture of the UNMODIFIED reference's own MNIST run (tests/golden/mnist_n2.pt).  The CUDA kernels themselves are
 checked against the same plain-torch statements in tests/test_mlp_gpu.py."""
+import os
+import sys
 from pathlib import Path
 
 import pytest
 import torch
 
-import mlp_ref_ops
+HERE = Path(__file__).resolve().parent
+for _p in (str(HERE.parent), str(HERE.parent / "distributed-gan_b200"), str(HERE)):   # spawned processes import this file
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import mlp_ref_ops  # noqa: E402
 from parity import build_actor_modules, l2err
 from util import plugin
 
@@ -146,3 +153,80 @@ def test_mlp_standalone_matches_oracle(monkeypatch):
     run.gen.state.store_to(run.G)
     flat = lambda sd: torch.cat([v.reshape(-1).double() for v in sd.values()])
     assert l2err(flat(run.G.state_dict()), flat(oracle.G.state_dict())) < 1e-4
+
+
+def _two_process_worker(proc, n_procs, port, out_dir, N, b, epochs, swap):
+    """One GPU-process stand-in of a 2-process gloo job, built the way bootstrap.init_process builds it: every hosted
+    worker actor on its own seed with its RNG stream handed over on the module, the server last."""
+    import torch.distributed as dist
+
+    import bootstrap
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200 import ops, routing
+    from mdgan_b200.engine import EngineConfig, MDGANEngine
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=proc, world_size=n_procs)
+    try:
+        for name in mlp_ref_ops.ALL:
+            setattr(ops, name, getattr(mlp_ref_ops, name))
+        torch.set_num_threads(1)
+        mod = plugin("MNIST")
+        data = SyntheticImages(mod.SHAPE, N * 4 * b)
+        local = routing.workers_of_process(proc, n_procs, N)
+        discs = {}
+        for n in local:
+            bootstrap._seed_actor(3 + n + 1)
+            d = mod.Discriminator()
+            d.apply(bootstrap._weights_init)
+            d._mdgan_rng_state = torch.get_rng_state()
+            discs[n] = d
+        gen = None
+        if proc == 0:
+            bootstrap._seed_actor(3)
+            gen = mod.Generator()
+            gen.apply(bootstrap._weights_init)
+        cfg = EngineConfig(n_workers=N, batch_size=b, z_dim=mod.Z_DIM, image_shape=tuple(mod.SHAPE), swap_interval=swap,
+                           z_source="host", prefetch_host=True)
+        shards = routing.split_dataset(len(data), N, True)
+        src = {n: _HostBatches(routing.RealBatchStream(data, shards[n], b)) for n in local}
+        dev = torch.device("cpu")
+        eng = MDGANEngine(cfg, proc, n_procs, dev, gen, discs, src, factory=_CpuMlpFactory(dev))
+        losses = []
+        for e in range(epochs):
+            eng.iteration(e, last=(e == epochs - 1))
+            losses.append(eng.mean_d_loss())
+        eng.sync_modules()
+        torch.save({"G": None if gen is None else gen.state_dict(), "D": {n: discs[n].state_dict() for n in local},
+                    "losses": losses, "local": local}, Path(out_dir) / f"mlp_{proc}.pt")
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_mlp_two_process_gloo_run_matches_oracle(tmp_path):
+    """N > 1 processes (world_size-2 gloo, CPU): workers 1-2 with the server on process 0, workers 3-4 on process 1, each
+    worker's dropout stream continued from ITS actor seed wherever it is hosted, a swap across the process boundary."""
+    import torch.multiprocessing as mp
+
+    from datasets.DataPartitioner import SyntheticImages
+    from oracle.mdgan_oracle import OracleMDGAN
+
+    N, b, epochs, swap = 4, 4, 4, 2
+    port = 29100 + os.getpid() % 1500
+    mp.spawn(_two_process_worker, args=(2, port, str(tmp_path), N, b, epochs, swap), nprocs=2, join=True)
+    res = [torch.load(tmp_path / f"mlp_{p}.pt", weights_only=False) for p in range(2)]
+    torch.set_num_threads(1)
+    mod = plugin("MNIST")
+    oracle = OracleMDGAN(mod.Generator, mod.Discriminator, SyntheticImages(mod.SHAPE, N * 4 * b), N, b, mod.Z_DIM, mod.SHAPE,
+                         seed=3, beta_1=0.5, swap_interval=swap)
+    ref = [oracle.step(e, record=False) for e in range(epochs)]
+    assert any(r["pairs"] is not None for r in ref)
+    flat = lambda sd: torch.cat([v.reshape(-1).double() for v in sd.values()])
+    assert l2err(flat(res[0]["G"]), flat(oracle.G.state_dict())) < 1e-4
+    assert res[0]["local"] == [0, 1] and res[1]["local"] == [2, 3]
+    for r in res:
+        for i, n in enumerate(r["local"]):
+            assert l2err(flat(r["D"][n]), flat(oracle.D[n].state_dict())) < 1e-4, n
+            for e in range(epochs):
+                assert abs(r["losses"][e][i] - ref[e]["mean_d_loss"][n]) <= 1e-5 * abs(ref[e]["mean_d_loss"][n]), (e, n)
