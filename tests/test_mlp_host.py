@@ -230,3 +230,58 @@ def test_mlp_two_process_gloo_run_matches_oracle(tmp_path):
             assert l2err(flat(r["D"][n]), flat(oracle.D[n].state_dict())) < 1e-4, n
             for e in range(epochs):
                 assert abs(r["losses"][e][i] - ref[e]["mean_d_loss"][n]) <= 1e-5 * abs(ref[e]["mean_d_loss"][n]), (e, n)
+
+
+def test_mlp_plan_extraction_and_refusals():
+    """plan.extract_mlp_plan on the reference's MLP models, and the loud refusals (no fallback path)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    from mdgan_b200.plan import UnsupportedModelError, extract_mlp_plan, extract_plan, is_mlp
+
+    mod = plugin("MNIST")
+    torch.manual_seed(0)
+    d, g = mod.Discriminator(), mod.Generator()
+    before = torch.get_rng_state()
+    pd = extract_mlp_plan(d, "discriminator", mod.SHAPE)
+    pg = extract_mlp_plan(g, "generator", (mod.Z_DIM, 1, 1))
+    assert torch.equal(before, torch.get_rng_state()), "the dry run (which draws dropout masks) must not consume the RNG"
+    assert [(l.n_in, l.n_out, l.act, l.drop_p) for l in pd.layers] == [
+        (784, 1024, "lrelu", 0.3), (1024, 512, "lrelu", 0.3), (512, 256, "lrelu", 0.3), (256, 1, "sigmoid", 0.0)]
+    assert [(l.n_in, l.n_out, l.act, l.drop_p) for l in pg.layers] == [
+        (100, 256, "lrelu", 0.0), (256, 512, "lrelu", 0.0), (512, 1024, "lrelu", 0.0), (1024, 784, "tanh", 0.0)]
+    assert [l.weight for l in pd.layers] == ["fc1.weight", "fc2.weight", "fc3.weight", "fc4.weight"]
+    assert all(abs(l.slope - 0.2) < 1e-9 for l in pd.layers[:-1]) and pg.out_shape == (1, 28, 28) and pd.out_shape == ()
+    assert is_mlp(d) and is_mlp(g) and not is_mlp(plugin("CIFAR10").Discriminator())
+    with pytest.raises(UnsupportedModelError):
+        extract_plan(d, "discriminator", mod.SHAPE)              # the conv-family extractor refuses Linear layers
+
+    class ReluMlp(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Linear(784, 32), nn.Linear(32, 1)
+
+        def forward(self, x):
+            return torch.sigmoid(self.b(F.relu(self.a(x.view(x.shape[0], -1))))).flatten()
+
+    class NoSigmoid(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Linear(784, 32), nn.Linear(32, 1)
+
+        def forward(self, x):
+            return self.b(F.leaky_relu(self.a(x.view(x.shape[0], -1)), 0.2)).flatten()
+
+    class DropoutInGenerator(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Linear(100, 32), nn.Linear(32, 784)
+
+        def forward(self, z):
+            h = F.dropout(F.leaky_relu(self.a(z.view(z.shape[0], -1)), 0.2), 0.5)
+            return torch.tanh(self.b(h)).view(-1, 1, 28, 28)
+
+    for bad, role, shape in ((ReluMlp(), "discriminator", mod.SHAPE), (NoSigmoid(), "discriminator", mod.SHAPE),
+                             (DropoutInGenerator(), "generator", (100, 1, 1))):
+        with pytest.raises(UnsupportedModelError):
+            extract_mlp_plan(bad, role, shape)
