@@ -118,6 +118,8 @@ class MlpDiscNet:
                 self._host_fb[l].copy_(noise)
 
     def upload_host(self) -> None:
+        """Host mode: stage_host() + upload_host() must run before every iteration (engine.stage_inputs / upload_inputs
+        and standalone_gan.Standalone.step do); the step itself only reads the fixed device buffer."""
         if self.has_dropout:
             self.mask_dev.copy_(self.mask_host, non_blocking=True)
 
