@@ -3,20 +3,24 @@
 
     python bench.py --gpus 1 --steps K --warmup W              # our arm (sm_100a kernels), one process
     torchrun --nproc-per-node N ... bench.py --gpus N ...      # one rank per GPU over NCCL
-    python bench.py --impl reference ...                       # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference ...                       # the UNMODIFIED reference (oracle/_ref) on the host cores:
+                                                               # bootstrap.py --backend gloo --device cpu, N+1 processes
 
 Workload (DESIGN.md "Measurement"): MD-GAN with K = --gpus discriminator workers, one per GPU, the generator on
 rank 0 (north star "K=1/2/4/8 B200"), the reference's CelebA-shape 3x64x64 DCGAN, per-worker batch 64 (BASELINE.json
 configs[3], the largest configuration that fits one GPU); --dataset / --batch / --swap-interval select the other
-configurations.  The JSON line also carries `shapes`: the device-timed step of the MNIST-shape DCGAN (configs[1]) and
-of the CIFAR-10-shape DCGAN with a discriminator swap EVERY iteration inside the timed window (configs[2]).
+configurations.  The JSON line also carries `shapes`: the device-timed step of the MNIST-shape DCGAN (configs[1]), of
+the CIFAR-10-shape DCGAN with a discriminator swap EVERY iteration inside the timed window (configs[2]) and, at one
+GPU, of the reference's own MNIST plugin (the MLP with always-on dropout; device noise and masks).
 A step = one generator iteration: G forward over k*b noise vectors -> every worker's D step (real + X_d, Adam) and
 error feedback on X_g -> feedback sum/reduce -> one G backward -> G Adam.  Per-GPU work is fixed as the number of
 GPUs grows (one more worker per GPU), i.e. weak scaling; `value` is the whole-job rate
 generator-iterations/s x workers (worker-iterations/s), `generator_it_s` the plain rate.
 
-One JSON line on stdout (rank 0).  Keys beyond the base contract: roofline, cpu_baseline, e2e, clocks, gpu_launches,
-per_op (device-time share of every kernel family in one instrumented iteration).
+One JSON line on stdout (rank 0).  Keys beyond the base contract: roofline, cpu_baseline, e2e (MDGANEngine.iteration
+with HOST inputs -- host RNG noise, loader batches, pinned staging, H2D, losses read back every step; the next step's
+inputs are staged and uploaded while the current step runs), clocks, gpu_launches, per_op (device-time share of every
+kernel family in one instrumented iteration), multi_gpu_bit_identical (N > 1).
 """
 from __future__ import annotations
 
