@@ -285,3 +285,87 @@ def test_mlp_plan_extraction_and_refusals():
                              (DropoutInGenerator(), "generator", (100, 1, 1))):
         with pytest.raises(UnsupportedModelError):
             extract_mlp_plan(bad, role, shape)
+
+
+def _sharded_worker(proc, n_procs, port, out_dir, N, b, epochs, swap):
+    import torch.distributed as dist
+
+    import bootstrap
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200 import ops, routing
+    from mdgan_b200.engine import EngineConfig
+    from mdgan_b200.sharded import ShardedGeneratorEngine
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=proc, world_size=n_procs)
+    try:
+        for name in mlp_ref_ops.ALL:
+            setattr(ops, name, getattr(mlp_ref_ops, name))
+        torch.set_num_threads(1)
+        mod = plugin("MNIST")
+        data = SyntheticImages(mod.SHAPE, N * 4 * b)
+        local = routing.workers_of_process(proc, n_procs, N)
+        discs = {}
+        for n in local:
+            bootstrap._seed_actor(3 + n + 1)
+            d = mod.Discriminator()
+            d.apply(bootstrap._weights_init)
+            d._mdgan_rng_state = torch.get_rng_state()
+            discs[n] = d
+        bootstrap._seed_actor(3)            # the server's seed on EVERY process: identical generator replicas;
+        gen = mod.Generator()               # only process 0 goes on drawing from this stream (noise, swap pairs)
+        gen.apply(bootstrap._weights_init)
+        cfg = EngineConfig(n_workers=N, batch_size=b, z_dim=mod.Z_DIM, image_shape=tuple(mod.SHAPE), swap_interval=swap,
+                           z_source="host", prefetch_host=True)
+        shards = routing.split_dataset(len(data), N, True)
+        src = {n: _HostBatches(routing.RealBatchStream(data, shards[n], b)) for n in local}
+        dev = torch.device("cpu")
+        eng = ShardedGeneratorEngine(cfg, proc, n_procs, dev, gen, discs, src, factory=_CpuMlpFactory(dev))
+        assert eng.gen.n == 2 * b // n_procs
+        losses = []
+        for e in range(epochs):
+            eng.iteration(e, last=(e == epochs - 1))
+            losses.append(eng.mean_d_loss())
+        eng.sync_modules()
+        torch.save({"G": gen.state_dict(), "D": {n: discs[n].state_dict() for n in local}, "losses": losses, "local": local,
+                    "X": eng.X.clone()}, Path(out_dir) / f"sharded_{proc}.pt")
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_sharded_generator_two_processes(tmp_path):
+    """SURVEY n2 (protocol half, BatchNorm-free generators): every process runs G forward / backward on its k*b / P rows
+    of the noise batch -- noise broadcast, row blocks all-gathered, feedback all-reduced, gradients all-reduced, the same
+    Adam step everywhere -- and the job still reproduces the reference (oracle) to 1e-5, swaps included; the replicas
+    stay bit-identical to each other."""
+    import torch.multiprocessing as mp
+
+    from datasets.DataPartitioner import SyntheticImages
+    from mdgan_b200.sharded import ShardedGeneratorEngine
+    from oracle.mdgan_oracle import OracleMDGAN
+
+    N, b, epochs, swap = 4, 4, 4, 2
+    port = 29300 + os.getpid() % 1500
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path), N, b, epochs, swap), nprocs=2, join=True)
+    res = [torch.load(tmp_path / f"sharded_{p}.pt", weights_only=False) for p in range(2)]
+    torch.set_num_threads(1)
+    mod = plugin("MNIST")
+    oracle = OracleMDGAN(mod.Generator, mod.Discriminator, SyntheticImages(mod.SHAPE, N * 4 * b), N, b, mod.Z_DIM, mod.SHAPE,
+                         seed=3, beta_1=0.5, swap_interval=swap)
+    ref = [oracle.step(e, record=True) for e in range(epochs)]
+    flat = lambda sd: torch.cat([v.reshape(-1).double() for v in sd.values()])
+    assert all(torch.equal(res[0]["G"][k], res[1]["G"][k]) for k in res[0]["G"]), "generator replicas must stay identical"
+    assert torch.equal(res[0]["X"], res[1]["X"]) and l2err(res[0]["X"], ref[-1]["X"]) < 1e-5
+    assert l2err(flat(res[0]["G"]), flat(oracle.G.state_dict())) < 1e-4
+    for r in res:
+        for i, n in enumerate(r["local"]):
+            assert l2err(flat(r["D"][n]), flat(oracle.D[n].state_dict())) < 1e-4, n
+            for e in range(epochs):
+                assert abs(r["losses"][e][i] - ref[e]["mean_d_loss"][n]) <= 1e-5 * abs(ref[e]["mean_d_loss"][n]), (e, n)
+    # generators with BatchNorm couple the rows of the batch: refused until the cross-process statistics exist
+    from mdgan_b200.engine import EngineConfig
+    cif = plugin("CIFAR10")
+    cfg = EngineConfig(n_workers=2, batch_size=4, z_dim=cif.Z_DIM, image_shape=tuple(cif.SHAPE))
+    with pytest.raises(NotImplementedError):
+        ShardedGeneratorEngine(cfg, 0, 1, torch.device("cpu"), cif.Generator(), {}, {}, factory=_CpuMlpFactory(torch.device("cpu")))
