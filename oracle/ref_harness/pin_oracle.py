@@ -37,6 +37,10 @@ CASES = [
     ("celeba_n2", "distributed", "CelebA", 2, 4, 3, 10**6, 3),
     ("mnist_n2", "distributed", "MNIST", 2, 8, 3, 10**6, 3),
     ("cifar_standalone", "standalone", "CIFAR10", 0, 8, 3, 0, 1),
+    # the MLP plugin (always-on dropout drawn from each actor's global RNG stream) with swaps, and standalone (ONE stream
+    # shared by the loader seeds, the noise and the dropout draws)
+    ("mnist_n4_swap", "distributed", "MNIST", 4, 4, 4, 2, 3),
+    ("mnist_standalone", "standalone", "MNIST", 0, 8, 4, 0, 1),
 ]
 
 

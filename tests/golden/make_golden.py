@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generate tests/golden/*.pt from the UNMODIFIED reference, run in the build container (CPU, gloo).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]        # default: every case
 
 For each case of oracle/ref_harness/pin_oracle.py::CASES this runs the reference's own bootstrap.py /
 standalone_gan.py (N+1 processes, synthetic data), checks that the oracle restatement reproduces it, and stores a
@@ -37,8 +37,11 @@ def summarise(sd):
 
 
 def main():
+    only = sys.argv[1:]
     for case in pin_oracle.CASES:
         name, mode, dataset, workers, batch, epochs, swap_interval, seed = case
+        if only and name not in only:
+            continue
         r = pin_oracle.run_case(*case)
         assert r["G_maxdiff"] == 0.0 and r["D_maxdiff"] == 0.0 and r["loss_maxdiff"] < 1e-12 and r["swaps_bit_exact"], r
         out = Path(r["out"])
@@ -58,6 +61,7 @@ def main():
             fx["D"] = [summarise(torch.load(out / "weights" / f"netD_epoch_{epochs - 1}.pth"))]
             rows = list(csv.DictReader(open(out / "logs" / f"{dataset}.standalone.logs.csv")))
             fx["mean_d_loss"] = [[float(row["mean_d_loss"]) for row in rows]]
+            fx["mean_g_loss"] = [[float(row["mean_g_loss"]) for row in rows]]
         torch.save(fx, HERE / f"{name}.pt")
         size = (HERE / f"{name}.pt").stat().st_size
         print(f"{name}: reference == oracle bit-exact; fixture {size / 1024:.0f} kB", flush=True)

@@ -13,7 +13,7 @@ import torch
 from util import plugin
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-CASES = ["cifar_n2", "cifar_n4_swap", "celeba_n2", "mnist_n2", "cifar_standalone"]
+CASES = ["cifar_n2", "cifar_n4_swap", "celeba_n2", "mnist_n2", "cifar_standalone", "mnist_n4_swap", "mnist_standalone"]
 
 
 def _check_state(sd, fx, strict):
