@@ -41,7 +41,14 @@ CASES = [
     # shared by the loader seeds, the noise and the dropout draws)
     ("mnist_n4_swap", "distributed", "MNIST", 4, 4, 4, 2, 3),
     ("mnist_standalone", "standalone", "MNIST", 0, 8, 4, 0, 1),
+    # optional 9th field: extra launcher flags -- two local epochs per iteration, the non-iid (contiguous) split, a swap
+    ("cifar_n2_le2_noniid", "distributed", "CIFAR10", 2, 4, 3, 2, 3, {"local_epochs": 2, "iid": 0}),
 ]
+
+
+def case_args(case):
+    """(the 8 positional fields, the extras dict) of a CASES entry."""
+    return tuple(case[:8]), dict(case[8]) if len(case) > 8 else {}
 
 
 def _maxdiff(sd_a, sd_b):
@@ -52,7 +59,7 @@ def _maxdiff(sd_a, sd_b):
     return worst
 
 
-def run_case(name, mode, dataset, workers, batch, epochs, swap_interval, seed, keep=None):
+def run_case(name, mode, dataset, workers, batch, epochs, swap_interval, seed, keep=None, local_epochs=1, iid=1):
     torch.set_num_threads(1)
     out = Path(keep) if keep else Path(tempfile.mkdtemp(prefix=f"ref_{name}_"))
     m = max(workers, 1) * 16 * batch
@@ -60,7 +67,7 @@ def run_case(name, mode, dataset, workers, batch, epochs, swap_interval, seed, k
             "--epochs", str(epochs), "--seed", str(seed), "--out", str(out), "--threads", "1",
             "--beta_1", "0.5"]
     if mode == "distributed":
-        argv += ["--swap_interval", str(swap_interval)]
+        argv += ["--swap_interval", str(swap_interval), "--local_epochs", str(local_epochs), "--iid", str(iid)]
     sys.argv = ["run_reference.py"] + argv
     rc = run_reference.main()
     assert rc == 0, f"reference run failed for {name}"
@@ -71,7 +78,7 @@ def run_case(name, mode, dataset, workers, batch, epochs, swap_interval, seed, k
     res = {"name": name, "out": str(out)}
     if mode == "distributed":
         o = OracleMDGAN(mod.Generator, mod.Discriminator, ds, workers, batch, mod.Z_DIM, mod.SHAPE,
-                        seed=seed, beta_1=0.5, swap_interval=swap_interval)
+                        seed=seed, beta_1=0.5, swap_interval=swap_interval, local_epochs=local_epochs, iid=bool(iid))
         d_losses, pairs_log = [], []
         for e in range(epochs):
             r = o.step(e, record=False)
@@ -114,6 +121,7 @@ if __name__ == "__main__":
     for case in CASES:
         if only and case[0] not in only:
             continue
-        r = run_case(*case)
+        pos, extra = case_args(case)
+        r = run_case(*pos, **extra)
         print(f"{r['name']:18s} G_maxdiff={r['G_maxdiff']:.3e} D_maxdiff={r['D_maxdiff']:.3e} "
               f"loss_maxdiff={r['loss_maxdiff']:.3e} swaps_bit_exact={r['swaps_bit_exact']}", flush=True)

@@ -39,14 +39,15 @@ def summarise(sd):
 def main():
     only = sys.argv[1:]
     for case in pin_oracle.CASES:
-        name, mode, dataset, workers, batch, epochs, swap_interval, seed = case
+        pos, extra = pin_oracle.case_args(case)
+        name, mode, dataset, workers, batch, epochs, swap_interval, seed = pos
         if only and name not in only:
             continue
-        r = pin_oracle.run_case(*case)
+        r = pin_oracle.run_case(*pos, **extra)
         assert r["G_maxdiff"] == 0.0 and r["D_maxdiff"] == 0.0 and r["loss_maxdiff"] < 1e-12 and r["swaps_bit_exact"], r
         out = Path(r["out"])
         fx = {"case": dict(name=name, mode=mode, dataset=dataset, workers=workers, batch=batch, epochs=epochs,
-                           swap_interval=swap_interval, seed=seed, beta_1=0.5, samples=max(workers, 1) * 16 * batch),
+                           swap_interval=swap_interval, seed=seed, beta_1=0.5, samples=max(workers, 1) * 16 * batch, **extra),
               "stride": STRIDE, "torch": torch.__version__}
         if mode == "distributed":
             fx["G"] = summarise(torch.load(out / "weights" / "generator_final.pt"))

@@ -13,7 +13,8 @@ import torch
 from util import plugin
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-CASES = ["cifar_n2", "cifar_n4_swap", "celeba_n2", "mnist_n2", "cifar_standalone", "mnist_n4_swap", "mnist_standalone"]
+CASES = ["cifar_n2", "cifar_n4_swap", "celeba_n2", "mnist_n2", "cifar_standalone", "mnist_n4_swap", "mnist_standalone",
+         "cifar_n2_le2_noniid"]
 
 
 def _check_state(sd, fx, strict):
@@ -48,7 +49,8 @@ def test_oracle_reproduces_reference_run(name):
     ds = SyntheticImages(mod.SHAPE, c["samples"])
     if c["mode"] == "distributed":
         o = OracleMDGAN(mod.Generator, mod.Discriminator, ds, c["workers"], c["batch"], mod.Z_DIM, mod.SHAPE,
-                        seed=c["seed"], beta_1=c["beta_1"], swap_interval=c["swap_interval"])
+                        seed=c["seed"], beta_1=c["beta_1"], swap_interval=c["swap_interval"],
+                        local_epochs=c.get("local_epochs", 1), iid=bool(c.get("iid", 1)))
         for e in range(c["epochs"]):
             r = o.step(e, record=False)
             partner = {}
