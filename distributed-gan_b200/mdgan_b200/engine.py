@@ -124,13 +124,16 @@ class MDGANEngine:
         self.graph = None
         self._uploaded = None
         self._staged = False
-        # MDGAN_PREFETCH_H2D = 1 (default) | 0: with prefetch_host, the NEXT iteration's inputs are also copied to the
-        # device while the current iteration runs (copy stream -> shadow buffers; the iteration then starts with two
+        # MDGAN_PREFETCH_H2D = 1 (default) | force | 0: with prefetch_host, the NEXT iteration's inputs are also copied to
+        # the device while the current iteration runs (copy stream -> shadow buffers; the iteration then starts with two
         # device-to-device copies instead of waiting for PCIe).  See upload_ahead / upload_inputs.
-        # Nets with host-staged inputs of their own (the MLP family's dropout masks, mlp_nets.MlpDiscNet.stage_host) use
+        # "1" enables it on single-process runs, where it was validated (bit-identity test, A/B in profiles/); multi-GPU
+        # jobs keep the compute-stream upload they were validated with until "force" has been exercised on a multi-GPU
+        # box.  Nets with host-staged inputs of their own (the MLP family's dropout masks, MlpDiscNet.stage_host) use
         # the plain upload.
+        h2d = os.environ.get("MDGAN_PREFETCH_H2D", "1")
         self._h2d_ahead = (cfg.prefetch_host and device.type == "cuda"
-                           and os.environ.get("MDGAN_PREFETCH_H2D", "1") == "1"
+                           and (h2d == "force" or (h2d == "1" and n_procs == 1))
                            and not any(getattr(d, "stage_host", None) is not None for d in self.disc.values()))
         self._copy_stream = None
         self._ahead = False          # the shadow buffers hold the next iteration's inputs
