@@ -548,8 +548,12 @@ def run_ours(args) -> None:
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(local),
            "api": "MDGANEngine.iteration (the loop body of actors.server.start / actors.worker.start): host torch RNG "
                   "noise + host DataLoader batches -> pinned -> device, losses read back every iteration; the host staging "
-                  "and the H2D copy of step i+1 run while step i computes (copy stream -> shadow buffers, adopted "
-                  "device-to-device at the start of step i+1; MDGAN_PREFETCH_H2D=0 uploads on the compute stream)"}
+                  "of step i+1 runs while step i computes" + (
+                      " and so does its H2D copy (copy stream -> shadow buffers, adopted device-to-device at the start "
+                      "of step i+1; MDGAN_PREFETCH_H2D=0 uploads on the compute stream)"
+                      if getattr(engine, "_h2d_ahead", False) else
+                      "; the H2D copy is on the compute stream (the early upload is on by default for single-process "
+                      "runs only, MDGAN_PREFETCH_H2D=force)")}
     engine.close()
     del engine
 
